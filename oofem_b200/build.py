@@ -1,0 +1,48 @@
+"""Build liboofem_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liboofem_b200.so")
+SOURCES = ["context.cu", "csr.cu", "element_kernels.cu", "cg.cu", "comm.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "oofem_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        cmd = [nvcc, "-c", os.path.join(CSRC, s), "-o", o] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    fail = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode or verbose:
+            print(f"--- {s}\n{out}")
+        fail |= p.returncode != 0
+    if fail:
+        raise RuntimeError("nvcc failed")
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,388 @@
+// SparseLinearSystemNM "cudacg": the IML++ preconditioned CG template (iml/cg.h:23-72) as
+// IMLSolver::solve instantiates it (src/core/iml/imlsolver.C:101-146) with DiagPreconditioner
+// (src/core/iml/diagpre.C) or VoidPreconditioner.
+//
+// All scalars (rho, alpha, beta, residual, the convergence flag) stay on the device; kernels
+// become no-ops once the flag is set, so the host enqueues iterations ahead and polls the flag
+// every few iterations -- the result is identical to stopping exactly at the reference's test
+//   if ((resid = norm(r) / normb) <= tol) return   (cg.h:36, cg.h:60).
+// Reductions are two-stage (per-block partials in a fixed order, then one block) and therefore
+// deterministic run to run.
+#include "common.cuh"
+#include "elemset.h"
+#include "comm.h"
+
+namespace ob200 {
+
+int spmv(ob200_csr *A, const double *x, double *y);
+
+struct CgScalars {
+    double normb, rho, rho_1, alpha, beta, resid;
+    int iters, done;
+};
+
+constexpr int kRedMax = 3;            // simultaneous reductions
+constexpr int kCgThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double s)
+{
+#pragma unroll
+    for ( int o = 16; o > 0; o >>= 1 ) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// block-level sum; result valid in thread 0
+__device__ __forceinline__ double block_sum(double s, double *scratch /* [32] */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    s = warp_sum(s);
+    __syncthreads();
+    if ( lane == 0 ) scratch[wid] = s;
+    __syncthreads();
+    if ( wid == 0 ) {
+        s = lane < ( blockDim.x >> 5 ) ? scratch[lane] : 0.0;
+        s = warp_sum(s);
+    }
+    return s;
+}
+
+// DiagPreconditioner::init (diagpre.C:41-58): diag = 1 / A(i,i); zero diagonal is an error
+__global__ void diag_init_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                 const double *__restrict__ val, double *__restrict__ diag, int *__restrict__ bad)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        int lo = rowptr[i], hi = rowptr[i + 1] - 1;
+        double d = 0.0;
+        while ( lo <= hi ) {
+            int mid = ( lo + hi ) >> 1;
+            int v = colind[mid];
+            if ( v == i ) { d = val[mid]; break; }
+            if ( v < i ) lo = mid + 1; else hi = mid - 1;
+        }
+        if ( d == 0.0 ) atomicAdd(bad, 1);
+        diag[i] = 1.0 / d;
+    }
+}
+
+// sub-assembled (distributed) diagonal: raw A(i,i), to be summed over partitions before inversion
+__global__ void diag_extract_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                    const double *__restrict__ val, double *__restrict__ diag)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        int lo = rowptr[i], hi = rowptr[i + 1] - 1;
+        double d = 0.0;
+        while ( lo <= hi ) {
+            int mid = ( lo + hi ) >> 1;
+            int v = colind[mid];
+            if ( v == i ) { d = val[mid]; break; }
+            if ( v < i ) lo = mid + 1; else hi = mid - 1;
+        }
+        diag[i] = d;
+    }
+}
+
+__global__ void diag_invert_kernel(int32_t neq, double *__restrict__ diag, int *__restrict__ bad)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        double d = diag[i];
+        if ( d == 0.0 ) atomicAdd(bad, 1);
+        diag[i] = 1.0 / d;
+    }
+}
+
+// q = A p (warp per row) with the partial sums of p.q fused in (cg.h:53-54).
+// FUSE_DOT = false: plain product (distributed path adds the halo before the dot).
+template< bool FUSE_DOT >
+__global__ void __launch_bounds__(kCgThreads)
+cg_spmv_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+               const double *__restrict__ val, const double *__restrict__ p, double *__restrict__ q,
+               double *__restrict__ partials, const CgScalars *__restrict__ S)
+{
+    __shared__ double scratch[32];
+    if ( S->done ) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    double pq = 0.0;
+    for ( int64_t row = warp0; row < neq; row += nwarps ) {
+        const int b = rowptr[row], e = rowptr[row + 1];
+        double s = 0.0;
+        for ( int t = b + lane; t < e; t += 32 ) s += val[t] * p[colind[t]];
+        s = warp_sum(s);
+        if ( lane == 0 ) {
+            q[row] = s;
+            if ( FUSE_DOT ) pq += s * p[row];
+        }
+    }
+    if ( FUSE_DOT ) {
+        pq = block_sum(pq, scratch);
+        if ( threadIdx.x == 0 ) partials[blockIdx.x] = pq;
+    }
+}
+
+// r = b - q (q = A x already, halo-summed), partials of b.b, r.r, r.z with z = M^-1 r   (cg.h:32-33)
+__global__ void __launch_bounds__(kCgThreads)
+cg_init_kernel(int32_t neq, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
+               const double *__restrict__ diag, const unsigned char *__restrict__ owned,
+               double *__restrict__ partials, int P)
+{
+    __shared__ double scratch[32];
+    double bb = 0.0, rr = 0.0, rz = 0.0;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        double bi = b[i], ri = bi - q[i];
+        r[i] = ri;
+        if ( !owned || owned[i] ) {
+            bb += bi * bi;
+            rr += ri * ri;
+            rz += ri * ( diag ? ri * diag[i] : ri );
+        }
+    }
+    bb = block_sum(bb, scratch);
+    if ( threadIdx.x == 0 ) partials[blockIdx.x] = bb;
+    rr = block_sum(rr, scratch);
+    if ( threadIdx.x == 0 ) partials[P + blockIdx.x] = rr;
+    rz = block_sum(rz, scratch);
+    if ( threadIdx.x == 0 ) partials[2 * P + blockIdx.x] = rz;
+}
+
+// p = z (first iteration) or p = z + beta p, z = M.solve(r)      (cg.h:45-52, diagpre.C:61-68)
+__global__ void __launch_bounds__(kCgThreads)
+cg_update_p_kernel(int32_t neq, const double *__restrict__ r, const double *__restrict__ diag,
+                   double *__restrict__ p, int first, const CgScalars *__restrict__ S)
+{
+    if ( S->done ) return;
+    const double beta = S->beta;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        double z = diag ? r[i] * diag[i] : r[i];
+        p[i] = first ? z : z + beta * p[i];
+    }
+}
+
+// x += alpha p; r -= alpha q; partials of r.r and r.z for the next test / rho       (cg.h:56-58)
+__global__ void __launch_bounds__(kCgThreads)
+cg_update_xr_kernel(int32_t neq, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                    const double *__restrict__ q, const double *__restrict__ diag,
+                    const unsigned char *__restrict__ owned, double *__restrict__ partials, int P,
+                    const CgScalars *__restrict__ S)
+{
+    __shared__ double scratch[32];
+    if ( S->done ) return;
+    const double alpha = S->alpha;
+    double rr = 0.0, rz = 0.0;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        x[i] += alpha * p[i];
+        double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        if ( !owned || owned[i] ) {
+            rr += ri * ri;
+            rz += ri * ( diag ? ri * diag[i] : ri );
+        }
+    }
+    rr = block_sum(rr, scratch);
+    if ( threadIdx.x == 0 ) partials[blockIdx.x] = rr;
+    rz = block_sum(rz, scratch);
+    if ( threadIdx.x == 0 ) partials[P + blockIdx.x] = rz;
+}
+
+// masked dot product partials (distributed path: p.q after the halo sum)
+__global__ void __launch_bounds__(kCgThreads)
+cg_dot_kernel(int32_t neq, const double *__restrict__ a, const double *__restrict__ b,
+              const unsigned char *__restrict__ owned, double *__restrict__ partials, const CgScalars *__restrict__ S)
+{
+    __shared__ double scratch[32];
+    if ( S->done ) return;
+    double s = 0.0;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride )
+        if ( !owned || owned[i] ) s += a[i] * b[i];
+    s = block_sum(s, scratch);
+    if ( threadIdx.x == 0 ) partials[blockIdx.x] = s;
+}
+
+// second reduction stage: red[k] = sum_b partials[k*P + b], fixed order
+__global__ void __launch_bounds__(kCgThreads)
+cg_reduce_kernel(const double *__restrict__ partials, int P, int nred, double *__restrict__ red, const CgScalars *__restrict__ S)
+{
+    __shared__ double scratch[32];
+    if ( S->done ) return;
+    for ( int k = 0; k < nred; k++ ) {
+        double s = 0.0;
+        for ( int i = threadIdx.x; i < P; i += blockDim.x ) s += partials[k * P + i];
+        s = block_sum(s, scratch);
+        if ( threadIdx.x == 0 ) red[k] = s;
+    }
+}
+
+// stage 0 (init):  red = {b.b, r.r, r.z};  stage 1 (after SpMV): red = {p.q};
+// stage 2 (after x/r update of iteration `iter`): red = {r.r, r.z}
+__global__ void cg_scalars_kernel(int stage, int iter, double tol, const double *__restrict__ red, CgScalars *S)
+{
+    if ( S->done ) return;
+    if ( stage == 1 ) {
+        S->alpha = S->rho / red[0];                       // alpha = rho / dot(p, q)     (cg.h:54)
+        return;
+    }
+    double rr, rz;
+    if ( stage == 0 ) {
+        double normb = sqrt(red[0]);                      // Real normb = norm(b)        (cg.h:31)
+        if ( normb == 0.0 ) normb = 1;                    //                              (cg.h:34-35)
+        S->normb = normb;
+        rr = red[1];
+        rz = red[2];
+    } else {
+        rr = red[0];
+        rz = red[1];
+    }
+    double resid = sqrt(rr) / S->normb;
+    S->resid = resid;
+    if ( resid <= tol ) {                                 // (cg.h:37-41, 60-64)
+        S->done = 1;
+        S->iters = iter;
+        return;
+    }
+    S->rho_1 = S->rho;                                    // rho_1 = rho                  (cg.h:66)
+    S->rho = rz;                                          // rho = dot(r, z)              (cg.h:47)
+    S->beta = S->rho / S->rho_1;                          // beta = rho / rho_1           (cg.h:51)
+    S->iters = iter;
+}
+
+struct CgWork {
+    double *r, *p, *q, *partials, *red;
+    CgScalars *S;
+};
+
+static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x_dev, int precond, int max_iter,
+                  double tol, int *iters, double *resid)
+{
+    ob200_context *ctx = A->ctx;
+    const int32_t n = A->neq;
+    const int P = ctx->shape.sms * 4;                   // blocks of every reducing kernel
+    const int64_t need = 3 * (int64_t) n + (int64_t) kRedMax * P + kRedMax + 16;
+    if ( A->work.n < need ) OB_CHECK( A->work.alloc(need) );
+    CgWork w;
+    w.r = A->work.p;
+    w.p = w.r + n;
+    w.q = w.p + n;
+    w.partials = w.q + n;
+    w.red = w.partials + (int64_t) kRedMax * P;
+    w.S = reinterpret_cast< CgScalars * >( w.red + kRedMax + 1 );
+    OB_CUDA( cudaMemsetAsync(w.partials, 0, sizeof( double ) * ( (size_t) kRedMax * P + kRedMax + 16 ), ctx->stream) );
+    const unsigned char *owned = comm ? comm->owned.p : nullptr;
+
+    // preconditioner (IMLSolver::solve re-inits when the matrix version changed, imlsolver.C:110-114)
+    const double *diag = nullptr;
+    if ( precond == OB200_PRECOND_DIAG ) {
+        if ( A->diag.n < n || A->diag_version != A->version || comm ) {
+            if ( A->diag.n < n ) OB_CHECK( A->diag.alloc(n > 0 ? n : 1) );
+            DevBuf< int > bad;
+            OB_CHECK( bad.alloc(1) );
+            OB_CUDA( cudaMemsetAsync(bad.p, 0, sizeof( int ), ctx->stream) );
+            if ( n ) {
+                int grid = ctx->shape.grid(n, 256, 8);
+                if ( !comm ) {
+                    OB_LAUNCH(ctx, diag_init_kernel, grid, 256, 0, n, A->rowptr.p, A->colind.p, A->val.p, A->diag.p, bad.p);
+                } else {
+                    OB_LAUNCH(ctx, diag_extract_kernel, grid, 256, 0, n, A->rowptr.p, A->colind.p, A->val.p, A->diag.p);
+                    OB_CHECK( comm_exchange_add(comm, A->diag.p) );
+                    OB_LAUNCH(ctx, diag_invert_kernel, grid, 256, 0, n, A->diag.p, bad.p);
+                }
+            }
+            int h = 0;
+            OB_CUDA( cudaMemcpyAsync(&h, bad.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
+            OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+            OB_REQUIRE(h == 0, OB200_EZERODIAG, "DiagPreconditioner: failed, zero diagonal detected in %d equations", h);
+            A->diag_version = A->version;
+        }
+        diag = A->diag.p;
+    } else {
+        OB_REQUIRE(precond == OB200_PRECOND_VOID, OB200_EINVAL, "cg_solve: unknown preconditioner type %d", precond);
+    }
+
+    auto reduce = [&](int nred) -> int {
+        OB_LAUNCH(ctx, cg_reduce_kernel, 1, kCgThreads, 0, w.partials, P, nred, w.red, w.S);
+        if ( comm ) OB_CHECK( comm_allreduce_sum(comm, w.red, nred) );
+        return OB200_OK;
+    };
+
+    // r = b - A x, resid test (cg.h:31-43)
+    OB_CHECK( spmv(A, x_dev, w.q) );
+    if ( comm ) OB_CHECK( comm_exchange_add(comm, w.q) );
+    OB_LAUNCH(ctx, cg_init_kernel, P, kCgThreads, 0, n, b_dev, w.q, w.r, diag, owned, w.partials, P);
+    OB_CHECK( reduce(3) );
+    OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 0, 0, tol, w.red, w.S);
+
+    CgScalars h;
+    const int poll = 8;
+    int it = 0;
+    bool done = false;
+    while ( !done ) {
+        int batch_end = it + poll < max_iter ? it + poll : max_iter;
+        for ( ; it < batch_end; ) {
+            it++;
+            OB_LAUNCH(ctx, cg_update_p_kernel, P, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
+            if ( !comm ) {
+                OB_LAUNCH(ctx, cg_spmv_kernel< true >, P, kCgThreads, 0, n, A->rowptr.p, A->colind.p, A->val.p, w.p, w.q, w.partials, w.S);
+            } else {
+                OB_LAUNCH(ctx, cg_spmv_kernel< false >, P, kCgThreads, 0, n, A->rowptr.p, A->colind.p, A->val.p, w.p, w.q, w.partials, w.S);
+                OB_CHECK( comm_exchange_add(comm, w.q) );
+                OB_LAUNCH(ctx, cg_dot_kernel, P, kCgThreads, 0, n, w.p, w.q, owned, w.partials, w.S);
+            }
+            OB_CHECK( reduce(1) );
+            OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 1, it, tol, w.red, w.S);
+            OB_LAUNCH(ctx, cg_update_xr_kernel, P, kCgThreads, 0, n, x_dev, w.r, w.p, w.q, diag, owned, w.partials, P, w.S);
+            OB_CHECK( reduce(2) );
+            OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 2, it, tol, w.red, w.S);
+        }
+        OB_CUDA( cudaMemcpyAsync(&h, w.S, sizeof( CgScalars ), cudaMemcpyDeviceToHost, ctx->stream) );
+        OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+        done = h.done || it >= max_iter;
+    }
+    *iters = h.done ? h.iters : max_iter;
+    *resid = h.resid;
+    return h.done ? 0 : 1;        // cg.h: 0 converged, 1 max_iter reached
+}
+
+} // namespace ob200
+
+using namespace ob200;
+
+static int cg_entry(ob200_csr *A, ob200_comm *comm, const double *b, double *x, int precond, int max_iter, double tol,
+                    int *iters, double *resid, int on_device)
+{
+    OB_REQUIRE(A && iters && resid, OB200_EINVAL, "cg_solve: null argument");
+    OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "cg_solve: matrix has no structure");
+    OB_REQUIRE(A->neq == 0 || ( b && x ), OB200_EINVAL, "cg_solve: size mismatch");       // imlsolver.C:105-107
+    OB_REQUIRE(max_iter >= 0, OB200_EINVAL, "cg_solve: negative max_iter");
+    Staged< double > B;
+    StagedOut< double > X;
+    OB_CHECK( B.stage(A->ctx, b, A->neq, on_device) );
+    OB_CHECK( X.stage(A->ctx, x, A->neq, on_device, true) );
+    int flag = cg_run(A, comm, B.d, X.d, precond, max_iter, tol, iters, resid);
+    if ( flag < 0 ) return flag;
+    OB_CHECK( X.finish(A->ctx) );
+    return flag;
+}
+
+extern "C" {
+
+int ob200_cg_solve(ob200_csr *A, const double *b, double *x, int precond, int max_iter, double tol, int *iters,
+                   double *resid, int on_device)
+{
+    return cg_entry(A, nullptr, b, x, precond, max_iter, tol, iters, resid, on_device);
+}
+
+int ob200_cg_solve_dist(ob200_csr *A, ob200_comm *c, const double *b, double *x, int precond, int max_iter, double tol,
+                        int *iters, double *resid, int on_device)
+{
+    OB_REQUIRE(c, OB200_EINVAL, "cg_solve_dist: null communicator");
+    OB_REQUIRE(c->neq == ( A ? A->neq : 0 ), OB200_EINVAL, "cg_solve_dist: halo describes %d equations, matrix has %d", c->neq, A ? A->neq : 0);
+    return cg_entry(A, c, b, x, precond, max_iter, tol, iters, resid, on_device);
+}
+
+} // extern "C"

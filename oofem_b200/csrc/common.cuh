@@ -1,0 +1,144 @@
+// Internal definitions shared by the translation units of liboofem_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/oofem_b200.h"
+
+namespace ob200 {
+
+void set_error(const char *fmt, ...);
+
+#define OB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if ( e__ != cudaSuccess ) {                                                            \
+            ob200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return OB200_ECUDA;                                                                \
+        }                                                                                      \
+    } while ( 0 )
+
+#define OB_CHECK(expr)                      \
+    do {                                    \
+        int rc__ = (expr);                  \
+        if ( rc__ < 0 ) return rc__;        \
+    } while ( 0 )
+
+#define OB_REQUIRE(cond, code, ...)         \
+    do {                                    \
+        if ( !( cond ) ) {                  \
+            ob200::set_error(__VA_ARGS__);  \
+            return code;                    \
+        }                                   \
+    } while ( 0 )
+
+constexpr int kWarp = 32;
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return ( a + b - 1 ) / b; }
+
+// grid for a grid-stride kernel: a whole number of waves on the device
+struct LaunchShape {
+    int sms = 148;
+    int grid(int64_t work_items, int block, int blocks_per_sm) const
+    {
+        int64_t need = ceil_div(work_items, block);
+        int64_t cap = (int64_t) sms * blocks_per_sm;
+        if ( need < 1 ) need = 1;
+        return (int)( need < cap ? need : cap );
+    }
+};
+
+// simple owning device buffer
+template< class T >
+struct DevBuf {
+    T *p = nullptr;
+    int64_t n = 0;
+    int alloc(int64_t count)
+    {
+        release();
+        n = count;
+        if ( count > 0 ) OB_CUDA( cudaMalloc(&p, sizeof( T ) * (size_t) count) );
+        return OB200_OK;
+    }
+    void release()
+    {
+        if ( p ) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+} // namespace ob200
+
+struct ob200_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    ob200::LaunchShape shape;
+    int64_t launches = 0;
+    // L2 flush scratch
+    ob200::DevBuf< char > flush;
+    // reduction scratch (partials) and small device scalars, used by CG
+    ob200::DevBuf< double > partials;
+};
+
+#define OB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                 \
+        kernel<<< ( grid ), ( block ), ( smem ), ( ctx )->stream >>>(__VA_ARGS__);       \
+        ( ctx )->launches++;                                                             \
+        OB_CUDA( cudaGetLastError() );                                                   \
+    } while ( 0 )
+
+// stage a host or device input in device memory; owns the copy when it came from the host
+template< class T >
+struct Staged {
+    const T *d = nullptr;
+    ob200::DevBuf< T > own;
+    int stage(ob200_context *ctx, const T *src, int64_t n, int on_device)
+    {
+        if ( on_device || n == 0 ) {
+            d = src;
+            return OB200_OK;
+        }
+        OB_CHECK( own.alloc(n) );
+        OB_CUDA( cudaMemcpyAsync(own.p, src, sizeof( T ) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream) );
+        d = own.p;
+        return OB200_OK;
+    }
+};
+
+// an output that lives on the device during the call and is copied back if the caller gave a host pointer
+template< class T >
+struct StagedOut {
+    T *d = nullptr;
+    T *host = nullptr;
+    int64_t n = 0;
+    ob200::DevBuf< T > own;
+    int stage(ob200_context *ctx, T *dst, int64_t count, int on_device, bool copy_in = false)
+    {
+        n = count;
+        if ( on_device || count == 0 ) {
+            d = dst;
+            return OB200_OK;
+        }
+        host = dst;
+        OB_CHECK( own.alloc(count) );
+        d = own.p;
+        if ( copy_in ) OB_CUDA( cudaMemcpyAsync(d, dst, sizeof( T ) * (size_t) count, cudaMemcpyHostToDevice, ctx->stream) );
+        return OB200_OK;
+    }
+    int finish(ob200_context *ctx)
+    {
+        if ( host && n > 0 ) {
+            OB_CUDA( cudaMemcpyAsync(host, d, sizeof( T ) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream) );
+            OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+        }
+        return OB200_OK;
+    }
+};

@@ -1,0 +1,130 @@
+// Context, error reporting and raw device-memory helpers of the C ABI.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace ob200 {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof( g_err ), fmt, ap);
+    va_end(ap);
+}
+
+__global__ void flush_kernel(char *p, int64_t n, char v)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x * 16;
+    for ( int64_t t = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) * 16; t + 16 <= n; t += stride )
+        *reinterpret_cast< int4 * >( p + t ) = make_int4(v, v, v, v);
+}
+} // namespace ob200
+
+using namespace ob200;
+
+extern "C" {
+
+const char *ob200_last_error(void) { return g_err; }
+const char *ob200_version(void) { return "oofem_b200 0.1 (sm_100a)"; }
+
+int ob200_context_create(int device, ob200_context **out)
+{
+    OB_REQUIRE(out, OB200_EINVAL, "context_create: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if ( e != cudaSuccess || n == 0 ) {
+        set_error("context_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return OB200_ENODEVICE;
+    }
+    OB_REQUIRE(device >= 0 && device < n, OB200_EINVAL, "context_create: device %d out of range [0,%d)", device, n);
+    OB_CUDA( cudaSetDevice(device) );
+    ob200_context *ctx = new ob200_context();
+    ctx->device = device;
+    if ( cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ) {
+        set_error("context_create: device query / stream creation failed");
+        delete ctx;
+        return OB200_ECUDA;
+    }
+    ctx->shape.sms = ctx->prop.multiProcessorCount;
+    *out = ctx;
+    return OB200_OK;
+}
+
+void ob200_context_destroy(ob200_context *ctx)
+{
+    if ( !ctx ) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->flush.release();
+    ctx->partials.release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int ob200_context_sync(ob200_context *ctx)
+{
+    OB_REQUIRE(ctx, OB200_EINVAL, "context_sync: null context");
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    return OB200_OK;
+}
+
+void *ob200_context_stream(ob200_context *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+int64_t ob200_context_launch_count(ob200_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int ob200_malloc(ob200_context *ctx, int64_t bytes, void **dptr)
+{
+    OB_REQUIRE(ctx && dptr && bytes >= 0, OB200_EINVAL, "malloc: bad argument");
+    OB_CUDA( cudaSetDevice(ctx->device) );
+    *dptr = nullptr;
+    if ( bytes ) OB_CUDA( cudaMalloc(dptr, (size_t) bytes) );
+    return OB200_OK;
+}
+
+int ob200_free(ob200_context *ctx, void *dptr)
+{
+    OB_REQUIRE(ctx, OB200_EINVAL, "free: null context");
+    if ( dptr ) {
+        OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+        OB_CUDA( cudaFree(dptr) );
+    }
+    return OB200_OK;
+}
+
+int ob200_memcpy_h2d(ob200_context *ctx, void *dst, const void *src, int64_t bytes)
+{
+    OB_REQUIRE(ctx && ( bytes == 0 || ( dst && src ) ), OB200_EINVAL, "memcpy_h2d: bad argument");
+    if ( bytes ) OB_CUDA( cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyHostToDevice, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    return OB200_OK;
+}
+
+int ob200_memcpy_d2h(ob200_context *ctx, void *dst, const void *src, int64_t bytes)
+{
+    OB_REQUIRE(ctx && ( bytes == 0 || ( dst && src ) ), OB200_EINVAL, "memcpy_d2h: bad argument");
+    if ( bytes ) OB_CUDA( cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    return OB200_OK;
+}
+
+int ob200_memset(ob200_context *ctx, void *dst, int value, int64_t bytes)
+{
+    OB_REQUIRE(ctx && ( bytes == 0 || dst ), OB200_EINVAL, "memset: bad argument");
+    if ( bytes ) OB_CUDA( cudaMemsetAsync(dst, value, (size_t) bytes, ctx->stream) );
+    return OB200_OK;
+}
+
+int ob200_flush_l2(ob200_context *ctx)
+{
+    OB_REQUIRE(ctx, OB200_EINVAL, "flush_l2: null context");
+    const int64_t bytes = (int64_t) 256 << 20;        // 256 MiB > 126 MB L2
+    if ( !ctx->flush.p ) OB_CHECK( ctx->flush.alloc(bytes) );
+    static char v = 0;
+    v++;
+    flush_kernel<<< ctx->shape.sms * 8, 256, 0, ctx->stream >>>(ctx->flush.p, bytes, v);
+    OB_CUDA( cudaGetLastError() );
+    return OB200_OK;
+}
+
+} // extern "C"

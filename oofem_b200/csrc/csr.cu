@@ -1,0 +1,389 @@
+// SparseMtrx "cudacsr": symbolic assembly (CompCol::buildInternalStructure), value assembly
+// (CompCol::assemble), SpMV (CompCol::times) -- reference: src/core/compcol.C.
+//
+// The pattern of a finite element matrix is structurally symmetric, so the reference's
+// compressed-column arrays (colptr, rowind) and the compressed-row arrays kept here
+// (rowptr, colind) are the same integers; values are stored by rows, A(i,j) at
+// val[rowptr[i] + k] with colind[rowptr[i] + k] == j.
+#include "common.cuh"
+#include "elemset.h"
+#include "scan.cuh"
+#include <limits.h>
+
+namespace ob200 {
+
+// ---- symbolic phase ---------------------------------------------------------------------
+
+// number of (element, local dof) incidences per equation
+__global__ void count_incidence_kernel(const int32_t *__restrict__ loc, int64_t n, int32_t neq,
+                                       int32_t *__restrict__ cnt, int *__restrict__ bad)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) {
+        int r = loc[t];
+        if ( r < 0 || r > neq ) atomicAdd(bad, 1);
+        else if ( r > 0 ) atomicAdd(cnt + r - 1, 1);
+    }
+}
+
+__global__ void fill_incidence_kernel(const int32_t *__restrict__ loc, int64_t n, int nd,
+                                      const int64_t *__restrict__ start, int32_t *__restrict__ fill,
+                                      int32_t *__restrict__ elems)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) {
+        int r = loc[t];
+        if ( r > 0 ) {
+            int k = atomicAdd(fill + r - 1, 1);
+            elems[start[r - 1] + k] = (int32_t)( t / nd );
+        }
+    }
+}
+
+// One warp per matrix row: gather the equation numbers of all elements touching the row into
+// shared memory, bitonic-sort, drop duplicates.  This is std::set<int> columns[jj-1].insert(ii-1)
+// of compcol.C:178-191 done row-parallel.  FILL = false counts, FILL = true writes colind.
+template< bool FILL >
+__global__ void row_pattern_kernel(const int32_t *__restrict__ loc, int nd, int32_t neq,
+                                   const int64_t *__restrict__ estart, const int32_t *__restrict__ elems,
+                                   int cap, int32_t *__restrict__ rowcount, const int32_t *__restrict__ rowptr,
+                                   int32_t *__restrict__ colind, int *__restrict__ overflow)
+{
+    extern __shared__ int32_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int32_t *buf = smem + (size_t) wid * cap;
+    for ( int64_t row = (int64_t) blockIdx.x * nw + wid; row < neq; row += (int64_t) gridDim.x * nw ) {
+        const int64_t e0 = estart[row], e1 = estart[row + 1];
+        const int64_t ncand = ( e1 - e0 ) * nd;
+        if ( ncand > cap ) {
+            if ( lane == 0 ) atomicAdd(overflow, 1);
+            continue;
+        }
+        int n2 = 32;
+        while ( n2 < ncand ) n2 <<= 1;
+        for ( int t = lane; t < n2; t += 32 ) {
+            int32_t v = INT_MAX;
+            if ( t < ncand ) {
+                int32_t e = elems[e0 + t / nd];
+                int32_t c = loc[(int64_t) e * nd + t % nd];
+                if ( c > 0 ) v = c - 1;
+            }
+            buf[t] = v;
+        }
+        __syncwarp();
+        for ( int k = 2; k <= n2; k <<= 1 )
+            for ( int j = k >> 1; j > 0; j >>= 1 ) {
+                for ( int t = lane; t < n2; t += 32 ) {
+                    int p = t ^ j;
+                    if ( p > t ) {
+                        int32_t a = buf[t], b = buf[p];
+                        bool up = ( ( t & k ) == 0 );
+                        if ( ( a > b ) == up ) { buf[t] = b; buf[p] = a; }
+                    }
+                }
+                __syncwarp();
+            }
+        // unique count / compaction (buf sorted ascending, INT_MAX padding last)
+        int base = 0;
+        const int32_t out0 = FILL ? rowptr[row] : 0;
+        for ( int t0 = 0; t0 < n2; t0 += 32 ) {
+            int t = t0 + lane;
+            int32_t v = buf[t];
+            bool keep = ( v != INT_MAX ) && ( t == 0 || buf[t - 1] != v );
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            if ( FILL && keep ) colind[out0 + base + __popc(m & ( ( 1u << lane ) - 1 ))] = v;
+            base += __popc(m);
+        }
+        if ( !FILL && lane == 0 ) rowcount[row] = base;
+        __syncwarp();
+    }
+}
+
+// ---- numeric phase ----------------------------------------------------------------------
+
+__device__ __forceinline__ int find_slot(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int r, int c)
+{
+    int lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while ( lo <= hi ) {
+        int mid = ( lo + hi ) >> 1;
+        int v = colind[mid];
+        if ( v == c ) return mid;
+        if ( v < c ) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+// CompCol::assemble(loc, mat) (compcol.C:263-299) for a batch of element matrices
+__global__ void csr_assemble_kernel(const int32_t *__restrict__ loc, const double *__restrict__ mat, int nd,
+                                    int64_t nelem, const int32_t *__restrict__ rowptr,
+                                    const int32_t *__restrict__ colind, double *__restrict__ val, int *__restrict__ missing)
+{
+    const int64_t total = nelem * nd * nd;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride ) {
+        int64_t e = t / ( nd * nd );
+        int ij = (int)( t - e * nd * nd );
+        int i = ij / nd, j = ij - i * nd;
+        int r = loc[e * nd + i], c = loc[e * nd + j];
+        if ( r > 0 && c > 0 ) {
+            int p = find_slot(rowptr, colind, r - 1, c - 1);
+            if ( p < 0 ) atomicAdd(missing, 1);
+            else atomicAdd(val + p, mat[t]);
+        }
+    }
+}
+
+__global__ void scale_kernel(double *__restrict__ v, int64_t n, double s)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) v[t] *= s;
+}
+
+// y = A x, one warp per row, coalesced loads of val / colind along the row, shuffle reduction.
+__global__ void __launch_bounds__(256)
+spmv_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+            const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    for ( int64_t row = warp0; row < neq; row += nwarps ) {
+        const int b = rowptr[row], e = rowptr[row + 1];
+        double s = 0.0;
+        for ( int t = b + lane; t < e; t += 32 ) s += val[t] * x[colind[t]];
+#pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ( lane == 0 ) y[row] = s;
+    }
+}
+
+} // namespace ob200
+
+using namespace ob200;
+
+void ob200_csr_touch(ob200_csr *A) { A->version++; }
+
+namespace ob200 {
+int spmv(ob200_csr *A, const double *x, double *y)
+{
+    if ( A->neq == 0 ) return OB200_OK;
+    int grid = A->ctx->shape.grid((int64_t) A->neq * 32, 256, 8);
+    OB_LAUNCH(A->ctx, spmv_kernel, grid, 256, 0, A->neq, A->rowptr.p, A->colind.p, A->val.p, x, y);
+    return OB200_OK;
+}
+} // namespace ob200
+
+extern "C" {
+
+int ob200_csr_create(ob200_context *ctx, ob200_csr **out)
+{
+    OB_REQUIRE(ctx && out, OB200_EINVAL, "csr_create: null argument");
+    ob200_csr *A = new ob200_csr();
+    A->ctx = ctx;
+    *out = A;
+    return OB200_OK;
+}
+
+void ob200_csr_destroy(ob200_csr *A) { delete A; }
+
+int32_t ob200_csr_rows(const ob200_csr *A) { return A ? A->neq : 0; }
+int64_t ob200_csr_nnz(const ob200_csr *A) { return A ? A->nnz : 0; }
+int64_t ob200_csr_version(const ob200_csr *A) { return A ? A->version : 0; }
+
+int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t nd, const int32_t *loc, int on_device)
+{
+    OB_REQUIRE(A && ( loc || nelem == 0 ), OB200_EINVAL, "csr_build_structure: null argument");
+    OB_REQUIRE(neq >= 0 && nelem >= 0 && nd > 0, OB200_EINVAL, "csr_build_structure: bad sizes neq=%d nelem=%lld nd=%d", neq, (long long) nelem, nd);
+    ob200_context *ctx = A->ctx;
+    Staged< int32_t > L;
+    OB_CHECK( L.stage(ctx, loc, nelem * nd, on_device) );
+    const int64_t ninc = nelem * nd;
+    OB_REQUIRE(ninc < (int64_t) INT_MAX, OB200_ECAPACITY, "csr_build_structure: %lld element dofs exceed the 32-bit index range", (long long) ninc);
+
+    DevBuf< int32_t > cnt, fill, elems, rowcount;
+    DevBuf< int64_t > estart, rp64;
+    DevBuf< int > flag;
+    OB_CHECK( cnt.alloc(neq + 1) );
+    OB_CHECK( fill.alloc(neq + 1) );
+    OB_CHECK( estart.alloc(neq + 1) );
+    OB_CHECK( flag.alloc(2) );
+    OB_CUDA( cudaMemsetAsync(cnt.p, 0, sizeof( int32_t ) * ( neq + 1 ), ctx->stream) );
+    OB_CUDA( cudaMemsetAsync(fill.p, 0, sizeof( int32_t ) * ( neq + 1 ), ctx->stream) );
+    OB_CUDA( cudaMemsetAsync(flag.p, 0, sizeof( int ) * 2, ctx->stream) );
+    if ( ninc ) {
+        int grid = ctx->shape.grid(ninc, 256, 8);
+        OB_LAUNCH(ctx, count_incidence_kernel, grid, 256, 0, L.d, ninc, neq, cnt.p, flag.p);
+    }
+    int hflag[2] = { 0, 0 };
+    OB_CUDA( cudaMemcpyAsync(hflag, flag.p, sizeof( int ) * 2, cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    OB_REQUIRE(hflag[0] == 0, OB200_EINVAL, "csr_build_structure: %d location entries outside [0, neq=%d]", hflag[0], neq);
+
+    int64_t total_inc = 0;
+    OB_CHECK( exclusive_scan(ctx, cnt.p, estart.p, (int64_t) neq + 1, &total_inc) );
+    OB_CHECK( elems.alloc(total_inc > 0 ? total_inc : 1) );
+    if ( ninc ) {
+        int grid = ctx->shape.grid(ninc, 256, 8);
+        OB_LAUNCH(ctx, fill_incidence_kernel, grid, 256, 0, L.d, ninc, nd, estart.p, fill.p, elems.p);
+    }
+    // largest candidate list decides the shared-memory capacity per warp
+    int32_t maxcnt = 0;
+    OB_CHECK( max_reduce(ctx, cnt.p, neq, &maxcnt) );
+    int64_t maxcand = (int64_t) maxcnt * nd;
+    int cap = 256;
+    while ( cap < maxcand ) cap <<= 1;
+    OB_REQUIRE(cap <= 8192, OB200_ECAPACITY,
+               "csr_build_structure: an equation couples to %lld candidate entries (> 8192 supported)", (long long) maxcand);
+    int warps = cap <= 1024 ? 8 : ( cap <= 4096 ? 4 : 2 );
+    size_t smem = (size_t) warps * cap * sizeof( int32_t );
+    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< false >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
+    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
+
+    OB_CHECK( rowcount.alloc(neq + 1) );
+    OB_CUDA( cudaMemsetAsync(rowcount.p, 0, sizeof( int32_t ) * ( neq + 1 ), ctx->stream) );
+    int pgrid = ctx->shape.grid((int64_t) neq * 32, warps * 32, 4);
+    if ( neq )
+        OB_LAUNCH(ctx, row_pattern_kernel< false >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
+                  rowcount.p, (const int32_t *) nullptr, (int32_t *) nullptr, flag.p + 1);
+    OB_CHECK( rp64.alloc(neq + 1) );
+    int64_t nnz = 0;
+    OB_CHECK( exclusive_scan(ctx, rowcount.p, rp64.p, (int64_t) neq + 1, &nnz) );
+    // CompCol stores colptr / rowind in IntArray (32-bit): keep the same limit and say so
+    OB_REQUIRE(nnz < (int64_t) INT_MAX, OB200_ECAPACITY, "csr_build_structure: nnz=%lld exceeds the 32-bit range of the reference's IntArray", (long long) nnz);
+    OB_CHECK( A->rowptr.alloc(neq + 1) );
+    OB_CHECK( narrow_i64_to_i32(ctx, rp64.p, A->rowptr.p, (int64_t) neq + 1) );
+    OB_CHECK( A->colind.alloc(nnz > 0 ? nnz : 1) );
+    OB_CHECK( A->val.alloc(nnz > 0 ? nnz : 1) );
+    if ( neq )
+        OB_LAUNCH(ctx, row_pattern_kernel< true >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
+                  (int32_t *) nullptr, A->rowptr.p, A->colind.p, flag.p + 1);
+    OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t)( nnz > 0 ? nnz : 1 ), ctx->stream) );
+    OB_CUDA( cudaMemcpyAsync(hflag, flag.p, sizeof( int ) * 2, cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    OB_REQUIRE(hflag[1] == 0, OB200_ECAPACITY, "csr_build_structure: internal row buffer overflow");
+    A->neq = neq;
+    A->nnz = nnz;
+    A->version++;
+    A->diag_version = -1;
+    return OB200_OK;
+}
+
+int ob200_csr_get_structure(const ob200_csr *A, int32_t *rowptr, int32_t *colind, int on_device)
+{
+    OB_REQUIRE(A && rowptr && colind, OB200_EINVAL, "csr_get_structure: null argument");
+    OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "csr_get_structure: matrix has no structure");
+    cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    OB_CUDA( cudaMemcpyAsync(rowptr, A->rowptr.p, sizeof( int32_t ) * ( A->neq + 1 ), k, A->ctx->stream) );
+    if ( A->nnz ) OB_CUDA( cudaMemcpyAsync(colind, A->colind.p, sizeof( int32_t ) * (size_t) A->nnz, k, A->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
+    return OB200_OK;
+}
+
+int ob200_csr_get_values(const ob200_csr *A, double *val, int on_device)
+{
+    OB_REQUIRE(A && val, OB200_EINVAL, "csr_get_values: null argument");
+    if ( A->nnz )
+        OB_CUDA( cudaMemcpyAsync(val, A->val.p, sizeof( double ) * (size_t) A->nnz,
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, A->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
+    return OB200_OK;
+}
+
+int ob200_csr_set_values(ob200_csr *A, const double *val, int on_device)
+{
+    OB_REQUIRE(A && val, OB200_EINVAL, "csr_set_values: null argument");
+    if ( A->nnz )
+        OB_CUDA( cudaMemcpyAsync(A->val.p, val, sizeof( double ) * (size_t) A->nnz,
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, A->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
+    A->version++;
+    return OB200_OK;
+}
+
+int ob200_csr_device_arrays(ob200_csr *A, const int32_t **rowptr, const int32_t **colind, double **val)
+{
+    OB_REQUIRE(A, OB200_EINVAL, "csr_device_arrays: null matrix");
+    if ( rowptr ) *rowptr = A->rowptr.p;
+    if ( colind ) *colind = A->colind.p;
+    if ( val ) *val = A->val.p;
+    return OB200_OK;
+}
+
+int ob200_csr_zero(ob200_csr *A)
+{
+    OB_REQUIRE(A, OB200_EINVAL, "csr_zero: null matrix");
+    if ( A->nnz ) OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t) A->nnz, A->ctx->stream) );
+    A->version++;
+    return OB200_OK;
+}
+
+int ob200_csr_scale(ob200_csr *A, double s)
+{
+    OB_REQUIRE(A, OB200_EINVAL, "csr_scale: null matrix");
+    if ( A->nnz ) {
+        int grid = A->ctx->shape.grid(A->nnz, 256, 8);
+        OB_LAUNCH(A->ctx, scale_kernel, grid, 256, 0, A->val.p, A->nnz, s);
+    }
+    A->version++;
+    return OB200_OK;
+}
+
+int ob200_csr_assemble(ob200_csr *A, int64_t nelem, int32_t nd, const int32_t *loc, const double *mat, int on_device)
+{
+    OB_REQUIRE(A && ( nelem == 0 || ( loc && mat ) ), OB200_EINVAL, "csr_assemble: null argument");
+    OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "csr_assemble: matrix has no structure");
+    OB_REQUIRE(nd > 0 && nelem >= 0, OB200_EINVAL, "csr_assemble: dimension of 'k' and 'loc' mismatch");
+    if ( nelem == 0 ) return OB200_OK;
+    ob200_context *ctx = A->ctx;
+    Staged< int32_t > L;
+    Staged< double > M;
+    OB_CHECK( L.stage(ctx, loc, nelem * nd, on_device) );
+    OB_CHECK( M.stage(ctx, mat, nelem * nd * nd, on_device) );
+    DevBuf< int > missing;
+    OB_CHECK( missing.alloc(1) );
+    OB_CUDA( cudaMemsetAsync(missing.p, 0, sizeof( int ), ctx->stream) );
+    int grid = ctx->shape.grid(nelem * nd * nd, 256, 8);
+    OB_LAUNCH(ctx, csr_assemble_kernel, grid, 256, 0, L.d, M.d, nd, nelem, A->rowptr.p, A->colind.p, A->val.p, missing.p);
+    int h = 0;
+    OB_CUDA( cudaMemcpyAsync(&h, missing.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    A->version++;
+    OB_REQUIRE(h == 0, OB200_ESTRUCT, "csr_assemble: couldn't find %d entries in the sparse structure", h);
+    return OB200_OK;
+}
+
+int ob200_csr_times(ob200_csr *A, const double *x, double *y, int on_device)
+{
+    OB_REQUIRE(A && ( A->neq == 0 || ( x && y ) ), OB200_EINVAL, "csr_times: null argument");
+    Staged< double > X;
+    StagedOut< double > Y;
+    OB_CHECK( X.stage(A->ctx, x, A->neq, on_device) );
+    OB_CHECK( Y.stage(A->ctx, y, A->neq, on_device) );
+    OB_CHECK( spmv(A, X.d, Y.d) );
+    return Y.finish(A->ctx);
+}
+
+int ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value)
+{
+    OB_REQUIRE(A && value, OB200_EINVAL, "csr_at: null argument");
+    // CompCol::at (compcol.C:376-390): "Array accessing exception -- out of bounds"
+    OB_REQUIRE(i >= 1 && j >= 1 && i <= A->neq && j <= A->neq, OB200_EINVAL, "csr_at: (%d,%d) out of bounds", i, j);
+    int32_t rp[2];
+    OB_CUDA( cudaMemcpyAsync(rp, A->rowptr.p + ( i - 1 ), sizeof( int32_t ) * 2, cudaMemcpyDeviceToHost, A->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
+    int n = rp[1] - rp[0];
+    *value = 0.0;
+    if ( n <= 0 ) return OB200_OK;
+    std::vector< int32_t > cols(n);
+    OB_CUDA( cudaMemcpyAsync(cols.data(), A->colind.p + rp[0], sizeof( int32_t ) * n, cudaMemcpyDeviceToHost, A->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
+    for ( int k = 0; k < n; k++ )
+        if ( cols[k] == j - 1 ) {
+            OB_CUDA( cudaMemcpyAsync(value, A->val.p + rp[0] + k, sizeof( double ), cudaMemcpyDeviceToHost, A->ctx->stream) );
+            OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
+            break;
+        }
+    return OB200_OK;
+}
+
+} // extern "C"

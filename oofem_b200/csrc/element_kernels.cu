@@ -1,0 +1,543 @@
+// Batched element evaluation: LSpace (warp per element) and LTRSpace (thread per element).
+//
+// Replaces the per-element loop of EngngModel::assemble / assembleVector
+// (src/core/engngm.C:889-929) over StructuralElement::computeStiffnessMatrix and
+// giveInternalForcesVector (src/sm/Elements/structuralelement.C:575-643, 724-802).
+#include "element_device.cuh"
+#include "elemset.h"
+
+namespace ob200 {
+
+constexpr int kHexWarps = 8;        // warps (= elements in flight) per CTA for the LSpace kernels
+
+// output modes of the stiffness kernels
+enum { OUT_KE = 0, OUT_CSR = 1, OUT_KDU = 2 };
+
+struct HexShared {
+    double xyz[24];          // vertex coordinates
+    double g[8][8][3];       // dN/dx per Gauss point and node
+    double dV[8];            // |det J| * weight
+    double D[8][36];         // per-GP tangent (MisesMat only)
+    double ue[24];           // element displacement vector (KDU / internal forces)
+    double sig[8][6];        // stresses (internal forces)
+};
+
+// Geometry phase shared by all LSpace kernels: lane = 4*gp + sub; every lane builds the Jacobian
+// of its Gauss point and the gradients of nodes 2*sub, 2*sub+1.
+__device__ __forceinline__ void hex_geometry(HexShared &s, int lane)
+{
+    int gp = lane >> 2, sub = lane & 3;
+    double u, v, w, Ji[3][3];
+    hexa_gp(gp, u, v, w);
+    double det = hexa_jacobian(s.xyz, u, v, w, Ji);
+#pragma unroll
+    for ( int n = 0; n < 2; n++ ) {
+        int k = 2 * sub + n;
+        double dN[3];
+        hexa_dNdxi(k, u, v, w, dN);
+#pragma unroll
+        for ( int j = 0; j < 3; j++ ) s.g[gp][k][j] = dN[0] * Ji[0][j] + dN[1] * Ji[1][j] + dN[2] * Ji[2][j];
+    }
+    if ( sub == 0 ) s.dV[gp] = fabs(det);      // weight 1*1*1 (structural3delement.C:328-338)
+}
+
+template< int MODE >
+__global__ void __launch_bounds__(kHexWarps * 32)
+lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot,
+                        const double *__restrict__ du, int64_t e_begin, int64_t e_end)
+{
+    __shared__ HexShared sh[kHexWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    HexShared &s = sh[wid];
+    const int64_t stride = (int64_t) gridDim.x * kHexWarps;
+    for ( int64_t e = e_begin + (int64_t) blockIdx.x * kHexWarps + wid; e < e_end; e += stride ) {
+        // stage connectivity -> coordinates through shared memory
+        if ( lane < 24 ) {
+            int node = S.conn[e * 8 + lane / 3] - 1;
+            s.xyz[lane] = S.coords[(int64_t) node * 3 + lane % 3];
+            if ( MODE == OUT_KDU ) s.ue[lane] = du[(int64_t) node * 3 + lane % 3];
+        }
+        __syncwarp();
+        hex_geometry(s, lane);
+        const MatParams mp = S.mat[S.matid[e]];
+        const bool mises = ( mp.type == (double) OB200_MAT_MISES );
+        if ( mises && lane < 8 ) mises_tangent(mp, &S.state[e * 8 + lane], s.D[lane]);
+        __syncwarp();
+        double lam, mu;
+        isole_lame(mp.E, mp.nu, lam, mu);
+#pragma unroll 1
+        for ( int t = lane; t < 64; t += 32 ) {
+            const int a = t >> 3, b = t & 7;
+            double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            if ( !mises ) {
+#pragma unroll
+                for ( int gp = 0; gp < 8; gp++ ) {
+                    double w = s.dV[gp];
+                    block_iso(acc, s.g[gp][a], s.g[gp][b], w * lam, w * mu);
+                }
+            } else {
+#pragma unroll 2
+                for ( int gp = 0; gp < 8; gp++ ) block_general(acc, s.g[gp][a], s.g[gp][b], s.D[gp], s.dV[gp]);
+            }
+            if ( MODE == OUT_KE ) {
+                double *o = out + e * 576 + ( 3 * a ) * 24 + 3 * b;
+#pragma unroll
+                for ( int i = 0; i < 3; i++ )
+#pragma unroll
+                    for ( int j = 0; j < 3; j++ ) o[i * 24 + j] = acc[3 * i + j];
+            } else if ( MODE == OUT_CSR ) {
+                const int32_t *sl = slot + e * 576 + ( 3 * a ) * 24 + 3 * b;
+#pragma unroll
+                for ( int i = 0; i < 3; i++ )
+#pragma unroll
+                    for ( int j = 0; j < 3; j++ ) {
+                        int32_t p = sl[i * 24 + j];
+                        if ( p >= 0 ) atomicAdd(out + p, acc[3 * i + j]);
+                    }
+            } else {   // f_a += K_ab du_b
+                const int32_t *loc = S.loc + e * 24 + 3 * a;
+#pragma unroll
+                for ( int i = 0; i < 3; i++ ) {
+                    double f = acc[3 * i] * s.ue[3 * b] + acc[3 * i + 1] * s.ue[3 * b + 1] + acc[3 * i + 2] * s.ue[3 * b + 2];
+                    int32_t r = loc[i];
+                    if ( r > 0 && f != 0.0 ) atomicAdd(out + r - 1, f);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Internal forces of LSpace elements.  fe != nullptr: write element vectors [nelem][24];
+// fglob != nullptr: scatter-add into the global vector through loc.
+__global__ void __launch_bounds__(kHexWarps * 32)
+lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
+                              double *__restrict__ fglob, double *__restrict__ gp_strain,
+                              double *__restrict__ gp_stress, int64_t e_begin, int64_t e_end)
+{
+    __shared__ HexShared sh[kHexWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    HexShared &s = sh[wid];
+    const int64_t stride = (int64_t) gridDim.x * kHexWarps;
+    for ( int64_t e = e_begin + (int64_t) blockIdx.x * kHexWarps + wid; e < e_end; e += stride ) {
+        if ( lane < 24 ) {
+            int node = S.conn[e * 8 + lane / 3] - 1;
+            s.xyz[lane] = S.coords[(int64_t) node * 3 + lane % 3];
+            s.ue[lane] = u[(int64_t) node * 3 + lane % 3];     // computeVectorOf(VM_Total)
+        }
+        __syncwarp();
+        hex_geometry(s, lane);
+        __syncwarp();
+        const MatParams mp = S.mat[S.matid[e]];
+        if ( lane < 8 ) {
+            const int gp = lane;
+            double eps[6] = { 0, 0, 0, 0, 0, 0 }, sig[6];
+#pragma unroll
+            for ( int k = 0; k < 8; k++ ) strain_add(eps, s.g[gp][k], &s.ue[3 * k]);   // strain = B u
+            if ( mp.type == (double) OB200_MAT_MISES ) {
+                mises_stress(mp, eps, &S.state[e * 8 + gp], sig);
+            } else {
+                double lam, mu;
+                isole_lame(mp.E, mp.nu, lam, mu);
+                iso_stress(lam, mu, eps, sig);          // LinearElasticMaterial::giveRealStressVector_3d
+            }
+#pragma unroll
+            for ( int i = 0; i < 6; i++ ) s.sig[gp][i] = sig[i];
+            if ( gp_strain )
+#pragma unroll
+                for ( int i = 0; i < 6; i++ ) gp_strain[( e * 8 + gp ) * 6 + i] = eps[i];
+            if ( gp_stress )
+#pragma unroll
+                for ( int i = 0; i < 6; i++ ) gp_stress[( e * 8 + gp ) * 6 + i] = sig[i];
+        }
+        __syncwarp();
+        if ( lane < 24 ) {     // answer.plusProduct(B, stress, dV): one dof per lane, Gauss points in order
+            const int k = lane / 3, c = lane % 3;
+            double f = 0.0;
+#pragma unroll
+            for ( int gp = 0; gp < 8; gp++ ) {
+                double fk[3];
+                force_node(fk, s.g[gp][k], s.sig[gp], s.dV[gp]);
+                f += ( c == 0 ? fk[0] : ( c == 1 ? fk[1] : fk[2] ) );
+            }
+            if ( fe ) fe[e * 24 + lane] = f;
+            if ( fglob ) {
+                int32_t r = S.loc[e * 24 + lane];
+                if ( r > 0 ) atomicAdd(fglob + r - 1, f);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- LTRSpace: one thread per element (1 Gauss point, constant gradients) ---------------
+
+__device__ __forceinline__ double tet_setup(const ElemSetView &S, int64_t e, double g[4][3], int node[4])
+{
+    double c[12];
+#pragma unroll
+    for ( int a = 0; a < 4; a++ ) {
+        node[a] = S.conn[e * 4 + a] - 1;
+#pragma unroll
+        for ( int j = 0; j < 3; j++ ) c[3 * a + j] = S.coords[(int64_t) node[a] * 3 + j];
+    }
+    double det = tet_dNdx(c, g);
+    return fabs(det) * ( 1.0 / 6.0 );     // gaussintegrationrule.C:500-507 weight 1/6
+}
+
+template< int MODE >
+__global__ void __launch_bounds__(128)
+ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot,
+                          const double *__restrict__ du, int64_t e_begin, int64_t e_end)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t e = e_begin + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += stride ) {
+        double g[4][3];
+        int node[4];
+        double dV = tet_setup(S, e, g, node);
+        const MatParams mp = S.mat[S.matid[e]];
+        const bool mises = ( mp.type == (double) OB200_MAT_MISES );
+        double D[36];
+        double lam, mu;
+        isole_lame(mp.E, mp.nu, lam, mu);
+        if ( mises ) mises_tangent(mp, &S.state[e], D);
+#pragma unroll 1
+        for ( int a = 0; a < 4; a++ ) {
+#pragma unroll 1
+            for ( int b = 0; b < 4; b++ ) {
+                double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+                if ( mises ) block_general(acc, g[a], g[b], D, dV);
+                else block_iso(acc, g[a], g[b], dV * lam, dV * mu);
+                if ( MODE == OUT_KE ) {
+                    double *o = out + e * 144 + ( 3 * a ) * 12 + 3 * b;
+#pragma unroll
+                    for ( int i = 0; i < 3; i++ )
+#pragma unroll
+                        for ( int j = 0; j < 3; j++ ) o[i * 12 + j] = acc[3 * i + j];
+                } else if ( MODE == OUT_CSR ) {
+                    const int32_t *sl = slot + e * 144 + ( 3 * a ) * 12 + 3 * b;
+#pragma unroll
+                    for ( int i = 0; i < 3; i++ )
+#pragma unroll
+                        for ( int j = 0; j < 3; j++ ) {
+                            int32_t p = sl[i * 12 + j];
+                            if ( p >= 0 ) atomicAdd(out + p, acc[3 * i + j]);
+                        }
+                } else {
+                    double ub[3] = { du[(int64_t) node[b] * 3], du[(int64_t) node[b] * 3 + 1], du[(int64_t) node[b] * 3 + 2] };
+#pragma unroll
+                    for ( int i = 0; i < 3; i++ ) {
+                        double f = acc[3 * i] * ub[0] + acc[3 * i + 1] * ub[1] + acc[3 * i + 2] * ub[2];
+                        int32_t r = S.loc[e * 12 + 3 * a + i];
+                        if ( r > 0 && f != 0.0 ) atomicAdd(out + r - 1, f);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
+                                double *__restrict__ fglob, double *__restrict__ gp_strain,
+                                double *__restrict__ gp_stress, int64_t e_begin, int64_t e_end)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t e = e_begin + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += stride ) {
+        double g[4][3];
+        int node[4];
+        double dV = tet_setup(S, e, g, node);
+        const MatParams mp = S.mat[S.matid[e]];
+        double eps[6] = { 0, 0, 0, 0, 0, 0 }, sig[6];
+#pragma unroll
+        for ( int a = 0; a < 4; a++ ) {
+            double ua[3] = { u[(int64_t) node[a] * 3], u[(int64_t) node[a] * 3 + 1], u[(int64_t) node[a] * 3 + 2] };
+            strain_add(eps, g[a], ua);
+        }
+        if ( mp.type == (double) OB200_MAT_MISES ) {
+            mises_stress(mp, eps, &S.state[e], sig);
+        } else {
+            double lam, mu;
+            isole_lame(mp.E, mp.nu, lam, mu);
+            iso_stress(lam, mu, eps, sig);
+        }
+        if ( gp_strain )
+#pragma unroll
+            for ( int i = 0; i < 6; i++ ) gp_strain[e * 6 + i] = eps[i];
+        if ( gp_stress )
+#pragma unroll
+            for ( int i = 0; i < 6; i++ ) gp_stress[e * 6 + i] = sig[i];
+#pragma unroll
+        for ( int a = 0; a < 4; a++ ) {
+            double fk[3];
+            force_node(fk, g[a], sig, dV);
+#pragma unroll
+            for ( int i = 0; i < 3; i++ ) {
+                if ( fe ) fe[e * 12 + 3 * a + i] = fk[i];
+                if ( fglob ) {
+                    int32_t r = S.loc[e * 12 + 3 * a + i];
+                    if ( r > 0 ) atomicAdd(fglob + r - 1, fk[i]);
+                }
+            }
+        }
+    }
+}
+
+// MaterialStatus::updateYourself: temp -> committed
+__global__ void mises_commit_kernel(MisesState *st, int64_t n)
+{
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n ) return;
+#pragma unroll
+    for ( int k = 0; k < 6; k++ ) st[i].plStrain[k] = st[i].tempPlStrain[k];
+    st[i].kappa = st[i].tempKappa;
+    st[i].damage = st[i].tempDamage;
+}
+
+// element -> CSR slot map: slot[e][i*nd+j] = position of A(loc_i, loc_j) in val, -1 if prescribed
+__global__ void slot_map_kernel(const int32_t *__restrict__ loc, int nd, int64_t nelem,
+                                const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                int32_t *__restrict__ slot, int *__restrict__ missing)
+{
+    const int64_t total = nelem * nd * nd;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride ) {
+        int64_t e = t / ( nd * nd );
+        int ij = (int)( t - e * nd * nd );
+        int i = ij / nd, j = ij - i * nd;
+        int r = loc[e * nd + i], c = loc[e * nd + j];
+        int32_t p = -1;
+        if ( r > 0 && c > 0 ) {
+            int lo = rowptr[r - 1], hi = rowptr[r] - 1, key = c - 1;
+            while ( lo <= hi ) {
+                int mid = ( lo + hi ) >> 1;
+                int v = colind[mid];
+                if ( v == key ) { p = mid; break; }
+                if ( v < key ) lo = mid + 1; else hi = mid - 1;
+            }
+            if ( p < 0 ) atomicAdd(missing, 1);
+        }
+        slot[t] = p;
+    }
+}
+
+// ---- host side of ob200_elemset ---------------------------------------------------------
+
+static int launch_stiffness(ob200_elemset *S, int mode, double *out, const int32_t *slot, const double *du)
+{
+    ob200_context *ctx = S->ctx;
+    ElemSetView v = S->view();
+    if ( S->nelem == 0 ) return OB200_OK;
+    if ( S->etype == OB200_LSPACE ) {
+        int grid = ctx->shape.grid(S->nelem * 32, kHexWarps * 32, 4);
+        if ( mode == OUT_KE ) OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_KE >, grid, kHexWarps * 32, 0, v, out, slot, du, 0, S->nelem);
+        else if ( mode == OUT_CSR ) OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_CSR >, grid, kHexWarps * 32, 0, v, out, slot, du, 0, S->nelem);
+        else OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_KDU >, grid, kHexWarps * 32, 0, v, out, slot, du, 0, S->nelem);
+    } else {
+        int grid = ctx->shape.grid(S->nelem, 128, 8);
+        if ( mode == OUT_KE ) OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_KE >, grid, 128, 0, v, out, slot, du, 0, S->nelem);
+        else if ( mode == OUT_CSR ) OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_CSR >, grid, 128, 0, v, out, slot, du, 0, S->nelem);
+        else OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_KDU >, grid, 128, 0, v, out, slot, du, 0, S->nelem);
+    }
+    return OB200_OK;
+}
+
+static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe, double *fglob, double *eps, double *sig)
+{
+    ob200_context *ctx = S->ctx;
+    ElemSetView v = S->view();
+    if ( S->nelem == 0 ) return OB200_OK;
+    if ( S->etype == OB200_LSPACE ) {
+        int grid = ctx->shape.grid(S->nelem * 32, kHexWarps * 32, 4);
+        OB_LAUNCH(ctx, lspace_internal_forces_kernel, grid, kHexWarps * 32, 0, v, u, fe, fglob, eps, sig, 0, S->nelem);
+    } else {
+        int grid = ctx->shape.grid(S->nelem, 128, 8);
+        OB_LAUNCH(ctx, ltrspace_internal_forces_kernel, grid, 128, 0, v, u, fe, fglob, eps, sig, 0, S->nelem);
+    }
+    return OB200_OK;
+}
+
+} // namespace ob200
+
+using namespace ob200;
+
+extern "C" {
+
+int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const double *coords, int64_t nelem,
+                         const int32_t *conn, const int32_t *matid, int32_t nmat, const double *matparams,
+                         const int32_t *loc, int32_t neq, int on_device, ob200_elemset **out)
+{
+    OB_REQUIRE(ctx && out, OB200_EINVAL, "elemset_create: null context/out");
+    OB_REQUIRE(etype == OB200_LSPACE || etype == OB200_LTRSPACE, OB200_EINVAL, "elemset_create: unknown element type %d", etype);
+    OB_REQUIRE(nnode >= 0 && nelem >= 0 && nmat >= 1, OB200_EINVAL, "elemset_create: negative size or no material");
+    ob200_elemset *S = new ob200_elemset();
+    S->ctx = ctx;
+    S->etype = etype;
+    S->nen = etype == OB200_LSPACE ? 8 : 4;
+    S->ngp = etype == OB200_LSPACE ? 8 : 1;
+    S->nd = 3 * S->nen;
+    S->nnode = nnode;
+    S->nelem = nelem;
+    S->nmat = nmat;
+    S->neq = neq;
+    int rc = OB200_OK;
+    auto put = [&](auto &buf, const auto *src, int64_t n) -> int {
+        OB_CHECK( buf.alloc(n) );
+        if ( n == 0 ) return OB200_OK;
+        OB_CUDA( cudaMemcpyAsync(buf.p, src, sizeof( *src ) * (size_t) n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream) );
+        return OB200_OK;
+    };
+    if ( ( rc = put(S->coords, coords, nnode * 3) ) < 0 || ( rc = put(S->conn, conn, nelem * S->nen) ) < 0 ||
+         ( rc = put(S->matid, matid, nelem) ) < 0 || ( rc = put(S->mat, matparams, (int64_t) nmat * OB200_MATPARAM_STRIDE) ) < 0 ||
+         ( rc = put(S->loc, loc, nelem * S->nd) ) < 0 ) {
+        delete S;
+        return rc;
+    }
+    // material state only when a MisesMat is present (host copy of the small parameter table decides)
+    std::vector< double > mp( (size_t) nmat * OB200_MATPARAM_STRIDE );
+    if ( cudaMemcpyAsync(mp.data(), S->mat.p, sizeof( double ) * mp.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+         cudaStreamSynchronize(ctx->stream) != cudaSuccess ) {
+        set_error("elemset_create: reading material table failed");
+        delete S;
+        return OB200_ECUDA;
+    }
+    for ( int m = 0; m < nmat; m++ ) {
+        int t = (int) mp[(size_t) m * OB200_MATPARAM_STRIDE];
+        if ( t != OB200_MAT_ISOLE && t != OB200_MAT_MISES ) {
+            set_error("elemset_create: unsupported material type %d", t);
+            delete S;
+            return OB200_EINVAL;
+        }
+        if ( t == OB200_MAT_MISES ) S->has_state = true;
+    }
+    if ( S->has_state ) {
+        int64_t n = nelem * S->ngp * OB200_MISES_STATE_DOUBLES;
+        if ( ( rc = S->state.alloc(n) ) < 0 ) { delete S; return rc; }
+        if ( n && cudaMemsetAsync(S->state.p, 0, sizeof( double ) * (size_t) n, ctx->stream) != cudaSuccess ) {
+            set_error("elemset_create: memset failed");
+            delete S;
+            return OB200_ECUDA;
+        }
+    }
+    *out = S;
+    return OB200_OK;
+}
+
+void ob200_elemset_destroy(ob200_elemset *S) { delete S; }
+
+int64_t ob200_elemset_size(const ob200_elemset *S) { return S ? S->nelem : 0; }
+
+int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
+{
+    OB_REQUIRE(S && Ke, OB200_EINVAL, "elemset_stiffness: null argument");
+    StagedOut< double > o;
+    OB_CHECK( o.stage(S->ctx, Ke, S->nelem * S->nd * S->nd, on_device) );
+    OB_CHECK( launch_stiffness(S, OUT_KE, o.d, nullptr, nullptr) );
+    return o.finish(S->ctx);
+}
+
+int ob200_elemset_internal_forces(ob200_elemset *S, const double *u, double *fe, double *gp_strain, double *gp_stress, int on_device)
+{
+    OB_REQUIRE(S && u && fe, OB200_EINVAL, "elemset_internal_forces: null argument");
+    Staged< double > du;
+    StagedOut< double > of, oe, os;
+    OB_CHECK( du.stage(S->ctx, u, S->nnode * 3, on_device) );
+    OB_CHECK( of.stage(S->ctx, fe, S->nelem * S->nd, on_device) );
+    if ( gp_strain ) OB_CHECK( oe.stage(S->ctx, gp_strain, S->nelem * S->ngp * 6, on_device) );
+    if ( gp_stress ) OB_CHECK( os.stage(S->ctx, gp_stress, S->nelem * S->ngp * 6, on_device) );
+    OB_CHECK( launch_internal_forces(S, du.d, of.d, nullptr, gp_strain ? oe.d : nullptr, gp_stress ? os.d : nullptr) );
+    OB_CHECK( of.finish(S->ctx) );
+    OB_CHECK( oe.finish(S->ctx) );
+    return os.finish(S->ctx);
+}
+
+int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
+{
+    OB_REQUIRE(S && A, OB200_EINVAL, "elemset_bind: null argument");
+    const int32_t *rowptr, *colind;
+    double *val;
+    OB_CHECK( ob200_csr_device_arrays(A, &rowptr, &colind, &val) );
+    OB_REQUIRE(rowptr, OB200_EINVAL, "elemset_bind: matrix has no structure (call ob200_csr_build_structure first)");
+    int64_t total = S->nelem * S->nd * S->nd;
+    OB_CHECK( S->slot.alloc(total) );
+    DevBuf< int > missing;
+    OB_CHECK( missing.alloc(1) );
+    OB_CUDA( cudaMemsetAsync(missing.p, 0, sizeof( int ), S->ctx->stream) );
+    if ( total ) {
+        int grid = S->ctx->shape.grid(total, 256, 8);
+        OB_LAUNCH(S->ctx, slot_map_kernel, grid, 256, 0, S->loc.p, S->nd, S->nelem, rowptr, colind, S->slot.p, missing.p);
+    }
+    int h = 0;
+    OB_CUDA( cudaMemcpyAsync(&h, missing.p, sizeof( int ), cudaMemcpyDeviceToHost, S->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
+    // CompCol::assemble DEBUG branch: "Couldn't find row %d in the sparse structure" (compcol.C:288-290)
+    OB_REQUIRE(h == 0, OB200_ESTRUCT, "elemset_bind: %d element entries are not in the sparse structure", h);
+    S->bound = A;
+    S->bound_version = ob200_csr_rows(A);
+    return OB200_OK;
+}
+
+int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
+{
+    OB_REQUIRE(S && A, OB200_EINVAL, "elemset_assemble_stiffness: null argument");
+    if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
+    const int32_t *rowptr, *colind;
+    double *val;
+    OB_CHECK( ob200_csr_device_arrays(A, &rowptr, &colind, &val) );
+    OB_CHECK( launch_stiffness(S, OUT_CSR, val, S->slot.p, nullptr) );
+    ob200_csr_touch(A);
+    return OB200_OK;
+}
+
+int ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, double *f, int on_device)
+{
+    OB_REQUIRE(S && u && f, OB200_EINVAL, "elemset_assemble_internal_forces: null argument");
+    Staged< double > du;
+    StagedOut< double > of;
+    OB_CHECK( du.stage(S->ctx, u, S->nnode * 3, on_device) );
+    OB_CHECK( of.stage(S->ctx, f, S->neq_hint(), on_device, true) );
+    OB_CHECK( launch_internal_forces(S, du.d, nullptr, of.d, nullptr, nullptr) );
+    return of.finish(S->ctx);
+}
+
+int ob200_elemset_assemble_extrapolated_forces(ob200_elemset *S, const double *du, double *f, int on_device)
+{
+    OB_REQUIRE(S && du && f, OB200_EINVAL, "elemset_assemble_extrapolated_forces: null argument");
+    Staged< double > d;
+    StagedOut< double > of;
+    OB_CHECK( d.stage(S->ctx, du, S->nnode * 3, on_device) );
+    OB_CHECK( of.stage(S->ctx, f, S->neq_hint(), on_device, true) );
+    OB_CHECK( launch_stiffness(S, OUT_KDU, of.d, nullptr, d.d) );
+    return of.finish(S->ctx);
+}
+
+int ob200_elemset_commit(ob200_elemset *S)
+{
+    OB_REQUIRE(S, OB200_EINVAL, "elemset_commit: null argument");
+    if ( !S->has_state ) return OB200_OK;
+    int64_t n = S->nelem * S->ngp;
+    if ( n ) OB_LAUNCH(S->ctx, mises_commit_kernel, (int) ceil_div(n, 256), 256, 0, (MisesState *) S->state.p, n);
+    return OB200_OK;
+}
+
+int ob200_elemset_get_state(ob200_elemset *S, double *state, int on_device)
+{
+    OB_REQUIRE(S && state, OB200_EINVAL, "elemset_get_state: null argument");
+    OB_REQUIRE(S->has_state, OB200_EINVAL, "elemset_get_state: element set has no MisesMat state");
+    OB_CUDA( cudaMemcpyAsync(state, S->state.p, sizeof( double ) * (size_t) S->state.n,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
+    return OB200_OK;
+}
+
+int ob200_elemset_set_state(ob200_elemset *S, const double *state, int on_device)
+{
+    OB_REQUIRE(S && state, OB200_EINVAL, "elemset_set_state: null argument");
+    OB_REQUIRE(S->has_state, OB200_EINVAL, "elemset_set_state: element set has no MisesMat state");
+    OB_CUDA( cudaMemcpyAsync(S->state.p, state, sizeof( double ) * (size_t) S->state.n,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S->ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
+    return OB200_OK;
+}
+
+} // extern "C"

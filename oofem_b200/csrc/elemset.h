@@ -1,0 +1,52 @@
+// Host-side objects behind the opaque C handles.
+#pragma once
+#include "common.cuh"
+
+namespace ob200 {
+struct MisesState;
+struct MatParams;
+
+// what the element kernels see
+struct ElemSetView {
+    const double *coords;      // [nnode][3]
+    const int32_t *conn;       // [nelem][nen], 1-based
+    const int32_t *matid;      // [nelem], 0-based
+    const MatParams *mat;      // [nmat]
+    const int32_t *loc;        // [nelem][nd], 1-based, 0 = prescribed
+    MisesState *state;         // [nelem*ngp] or nullptr
+};
+} // namespace ob200
+
+struct ob200_csr {
+    ob200_context *ctx = nullptr;
+    int32_t neq = 0;
+    int64_t nnz = 0;
+    int64_t version = 0;
+    ob200::DevBuf< int32_t > rowptr, colind;
+    ob200::DevBuf< double > val;
+    // CG work vectors (allocated on first solve)
+    ob200::DevBuf< double > work;
+    ob200::DevBuf< double > diag;
+    int64_t diag_version = -1;
+};
+
+struct ob200_elemset {
+    ob200_context *ctx = nullptr;
+    int etype = 0, nen = 0, ngp = 0, nd = 0;
+    int64_t nnode = 0, nelem = 0;
+    int32_t nmat = 0, neq = 0;
+    bool has_state = false;
+    ob200::DevBuf< double > coords, mat, state;
+    ob200::DevBuf< int32_t > conn, matid, loc, slot;
+    ob200_csr *bound = nullptr;
+    int64_t bound_version = -1;
+    int64_t neq_hint() const { return neq; }
+    ob200::ElemSetView view() const
+    {
+        return ob200::ElemSetView{ coords.p, conn.p, matid.p, (const ob200::MatParams *) mat.p, loc.p,
+                                   (ob200::MisesState *) state.p };
+    }
+};
+
+// bump the matrix version after its values changed (SparseMtrx::version)
+void ob200_csr_touch(ob200_csr *A);

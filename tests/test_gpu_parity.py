@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against
+ (1) the reference-generated golden fixtures (tests/golden/*.npz), and
+ (2) the CPU oracle on the same seeded inputs, at sizes the oracle finishes in seconds.
+
+Tolerances (BASELINE.json north_star): CSR rowptr / colind bit-exact; element matrices and
+internal forces 1e-12 relative (max-norm); converged displacements 1e-8 relative."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+from oofem_b200 import capi, meshgen
+from oofem_b200.elements import ElementSet
+from oofem_b200.engng import Domain, LinearStatic, StaticStructural
+from oofem_b200.inputfile import DirichletBC, Material, NodalLoad, Problem
+from oofem_b200.linsolver import CR_CONVERGED, CR_DIVERGED_ITS, CudaCG
+from oofem_b200.sparsemtrx import CudaCSR
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_KE = 1e-12
+TOL_U = 1e-8
+LINEAR = ["lspace_cantilever", "lspace_prescribed", "ltrspace_cantilever"]
+MISES = ["lspace_mises", "ltrspace_mises"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+# ---- against the reference's own output ------------------------------------------------
+
+@pytest.mark.parametrize("name", LINEAR + MISES)
+def test_csr_structure_bit_exact_vs_reference(ctx, name):
+    pb, d = load_golden(name)
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    rp, ci = A.structure()
+    assert np.array_equal(rp, d["colptr"])
+    assert np.array_equal(ci, d["rowind"])
+
+
+@pytest.mark.parametrize("name", LINEAR)
+def test_element_matrices_vs_reference(ctx, name):
+    pb, d = load_golden(name)
+    dom = Domain(ctx, pb)
+    Ke = dom.elems.computeStiffnessMatrix()
+    assert relerr(Ke.reshape(-1), d["elem_ke"]) < TOL_KE
+
+
+@pytest.mark.parametrize("name", LINEAR)
+def test_internal_forces_vs_reference(ctx, name):
+    pb, d = load_golden(name)
+    dom = Domain(ctx, pb)
+    u = d["node_u"].reshape(-1, 3)
+    fe = dom.elems.giveInternalForcesVector(u)
+    assert relerr(fe.reshape(-1), d["elem_fint"]) < TOL_KE
+
+
+@pytest.mark.parametrize("name", LINEAR)
+def test_assembled_values_and_spmv_vs_reference(ctx, name):
+    pb, d = load_golden(name)
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    dom.elems.assembleStiffness(A)
+    assert relerr(A.values(), d["val"]) < TOL_KE          # symmetric: CSR values == CompCol values
+    y = A.times(d["spmv_x"])
+    assert relerr(y, d["spmv_y"]) < TOL_KE
+    # SparseMtrx::at, 1-based
+    assert abs(A.at(1, 1) - d["val"][0]) <= TOL_KE * abs(d["val"]).max()
+    # per-element assemble(loc, mat) path gives the same matrix
+    B = CudaCSR(ctx)
+    B.buildInternalStructure(dom.loc, dom.neq)
+    Ke = d["elem_ke"].reshape(dom.loc.shape[0], dom.loc.shape[1], dom.loc.shape[1])
+    B.assemble(dom.loc[0], Ke[0])
+    B.assemble(dom.loc[1:], Ke[1:])
+    assert relerr(B.values(), d["val"]) < 1e-14
+
+
+@pytest.mark.parametrize("name", LINEAR)
+def test_linear_static_displacements_vs_reference(ctx, name):
+    pb, d = load_golden(name)
+    em = LinearStatic(ctx, pb)
+    u = em.solveYourselfAt(1.0)
+    assert relerr(u, d["node_u"].reshape(-1, 3)) < TOL_U
+
+
+@pytest.mark.parametrize("name", MISES)
+def test_mises_newton_vs_reference(ctx, name):
+    pb, d = load_golden(name)
+    em = StaticStructural(ctx, pb)
+    u = em.solveYourself()[-1]
+    assert relerr(u, d["node_u"].reshape(-1, 3)) < TOL_U
+    assert em.tangent_assemblies > len(em.iterations)      # tangent really re-assembled in the iterations
+    st = em.domain.elems.state()
+    assert (st[:, 6] > 0).any()                            # plastic flow happened
+    fe = em.domain.elems.giveInternalForcesVector(d["node_u"].reshape(-1, 3))
+    assert relerr(fe.reshape(-1), d["elem_fint"]) < TOL_U
+
+
+# ---- against the oracle on seeded inputs -------------------------------------------------
+
+def _random_problem(etype, nx, ny, nz, seed, mat):
+    gen = meshgen.hex_beam if etype == "lspace" else meshgen.tet_beam
+    lx = float(nx) / ny
+    coords, conn = gen(nx, ny, nz, lx, 1.0, 1.0)
+    fixed, tip = meshgen.cantilever_bcs(coords, lx)
+    coords = meshgen.perturb(coords, 0.3 / max(nx, ny, nz) / 2, seed=seed)
+    pb = Problem(engng="linearstatic", params=dict(nsteps=1, lstol=1e-13, lsiter=50000, lsprecond=1), coords=coords,
+                 elem_type=etype, conn=conn, elem_mat=np.zeros(conn.shape[0], np.int32), materials=[mat])
+    pb.ltfs[1] = ("const", 1.0)
+    pb.bcs.append(DirichletBC([1, 2, 3], [0.0, 0.0, 0.0], 1, fixed))
+    pb.loads.append(NodalLoad([1, 2, 3], [0.1, 0.2, -1.0], 1, tip))
+    return pb
+
+
+@pytest.mark.parametrize("etype,dims", [("lspace", (12, 6, 5)), ("ltrspace", (8, 5, 4))])
+def test_full_path_vs_oracle(ctx, etype, dims):
+    pb = _random_problem(etype, *dims, seed=3, mat=Material("isole", 210e3, 0.3))
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    rp, ci = A.structure()
+    assert np.array_equal(rp, md.colptr) and np.array_equal(ci, md.rowind)           # bit-exact
+    Ke = dom.elems.computeStiffnessMatrix()
+    Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams)
+    assert relerr(Ke, Ke_o) < TOL_KE
+    dom.elems.assembleStiffness(A)
+    val_o = orc.compcol_assemble(md.loc, Ke_o, md.colptr, md.rowind)
+    assert relerr(A.values(), val_o) < TOL_KE
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=dom.neq)
+    assert relerr(A.times(x), orc.compcol_times(md.colptr, md.rowind, val_o, x)) < TOL_KE
+    u = rng.normal(size=pb.coords.shape) * 1e-3
+    fe = dom.elems.giveInternalForcesVector(u)
+    fe_o = orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams,
+                                     u[pb.conn - 1].reshape(pb.conn.shape[0], -1))
+    assert relerr(fe, fe_o) < TOL_KE
+    f = np.zeros(dom.neq)
+    dom.elems.assembleInternalForces(u, f)
+    assert relerr(f, orc.assemble_vector(md.loc, fe_o, md.neq)) < TOL_KE
+    sol = orc.solve_linear_static(pb)
+    ug = LinearStatic(ctx, pb).solveYourselfAt(1.0)
+    assert relerr(ug, sol["u"]) < TOL_U
+
+
+@pytest.mark.parametrize("etype", ["lspace", "ltrspace"])
+def test_mises_material_point_vs_oracle(ctx, etype):
+    """Stress return, state update, algorithmic tangent and commit on random strains."""
+    mat = Material("misesmat", 210e3, 0.3, sig0=240.0, H=2100.0, omega_crit=0.2, a=30.0)
+    pb = _random_problem(etype, 5, 3, 3, seed=5, mat=mat)
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    rng = np.random.default_rng(1)
+    for scale in (2e-3, 6e-3, 4e-3):
+        u = rng.normal(size=pb.coords.shape) * scale
+        ue = u[pb.conn - 1].reshape(pb.conn.shape[0], -1)
+        fe, eps, sig = dom.elems.giveInternalForcesVector(u, want_gp=True)
+        fe_o, eps_o, sig_o = orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, ue,
+                                                       md.state, want_gp=True)
+        assert relerr(eps, eps_o) < TOL_KE and relerr(sig, sig_o) < TOL_KE and relerr(fe, fe_o) < TOL_KE
+        st = dom.elems.state()
+        assert (st[:, 14] > st[:, 6]).any()                   # some points are yielding
+        assert relerr(st, md.state) < TOL_KE
+        Ke = dom.elems.computeStiffnessMatrix()               # unsymmetric algorithmic tangent (damage on)
+        Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, md.state)
+        assert relerr(Ke, Ke_o) < TOL_KE
+        assert np.abs(Ke - Ke.transpose(0, 2, 1)).max() > 0.0
+        dom.elems.updateYourself()
+        orc.mises_commit(md.state)
+    # unsymmetric element matrices land transposed-correctly in the row storage
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    dom.elems.assembleStiffness(A)
+    val_cc = orc.compcol_assemble(md.loc, Ke_o, md.colptr, md.rowind)       # column storage
+    x = rng.normal(size=dom.neq)
+    assert relerr(A.times(x), orc.compcol_times(md.colptr, md.rowind, val_cc, x)) < TOL_KE
+
+
+def test_extrapolated_forces_vs_oracle(ctx):
+    pb = _random_problem("lspace", 6, 3, 3, seed=9, mat=Material("isole", 70e3, 0.25))
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    rng = np.random.default_rng(2)
+    du = rng.normal(size=pb.coords.shape) * 1e-3
+    f = np.zeros(dom.neq)
+    dom.elems.assembleExtrapolatedForces(du, f)
+    Ke = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams)
+    due = du[pb.conn - 1].reshape(pb.conn.shape[0], -1)
+    ref = orc.assemble_vector(md.loc, np.einsum("eij,ej->ei", Ke, due), md.neq)
+    assert relerr(f, ref) < TOL_KE
+
+
+# ---- solver semantics and edge cases -----------------------------------------------------
+
+def test_cg_iteration_semantics_match_iml(ctx):
+    """Same iteration count and residual as the IML template at a loose tolerance; flag 1 and
+    iters == max_iter when the budget is exhausted (iml/cg.h:70-71)."""
+    pb, d = load_golden("lspace_cantilever")
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    dom.elems.assembleStiffness(A)
+    b = np.ones(dom.neq)
+    for precond in (0, 1):
+        xo, flag_o, it_o, res_o = orc.cg(md.colptr, md.rowind, d["val"], b, precond=precond, max_iter=2000, tol=1e-6)
+        s = CudaCG(ctx).initializeFrom(dict(lstol=1e-6, lsiter=2000, lsprecond=precond))
+        x = np.zeros(dom.neq)
+        assert s.solve(A, b, x) == CR_CONVERGED and flag_o == 0
+        assert abs(s.last_iterations - it_o) <= 1
+        assert relerr(x, xo) < 1e-5
+    s = CudaCG(ctx).initializeFrom(dict(lstol=1e-14, lsiter=5, lsprecond=1))
+    x = np.zeros(dom.neq)
+    assert s.solve(A, b, x) == CR_DIVERGED_ITS and s.last_iterations == 5 and s.last_residual > 1e-14
+    # initial guess already the solution: zero iterations (cg.h:36-41)
+    s = CudaCG(ctx).initializeFrom(dict(lstol=1e-6, lsiter=100, lsprecond=1))
+    x = xo.copy()
+    assert s.solve(A, b, x) == CR_CONVERGED and s.last_iterations == 0
+    # zero right-hand side: normb := 1, x stays 0
+    x = np.zeros(dom.neq)
+    assert s.solve(A, np.zeros(dom.neq), x) == CR_CONVERGED and s.last_iterations == 0 and not x.any()
+
+
+def test_error_behaviour(ctx):
+    pb, d = load_golden("ltrspace_cantilever")
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc[:10], dom.neq)            # structure from a subset of the elements
+    with pytest.raises(capi.OofemB200Error) as ei:             # entries outside the structure
+        dom.elems.assembleStiffness(A)
+    assert ei.value.code == capi.ESTRUCT
+    with pytest.raises(capi.OofemB200Error):                   # incompatible dimensions in times()
+        A.times(np.zeros(dom.neq + 1))
+    with pytest.raises(capi.OofemB200Error) as ei:             # at() out of bounds
+        A.at(dom.neq + 1, 1)
+    assert ei.value.code == capi.EINVAL
+    Z = CudaCSR(ctx)
+    Z.buildInternalStructure(dom.loc, dom.neq)                 # all-zero matrix: zero diagonal in DiagPreconditioner
+    with pytest.raises(capi.OofemB200Error) as ei:
+        CudaCG(ctx).initializeFrom(dict(lsprecond=1)).solve(Z, np.ones(dom.neq), np.zeros(dom.neq))
+    assert ei.value.code == capi.EZERODIAG
+    bad = dom.loc.copy()
+    bad[0, 0] = dom.neq + 5
+    with pytest.raises(capi.OofemB200Error):
+        CudaCSR(ctx).buildInternalStructure(bad, dom.neq)
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(np.zeros((0, 24), np.int32), 0)
+    assert A.giveNumberOfRows() == 0 and A.giveNumberOfNonzeros() == 0
+    # every dof prescribed: elements exist, no equations
+    coords, conn = meshgen.hex_beam(2, 1, 1)
+    loc = np.zeros((2, 24), np.int32)
+    A.buildInternalStructure(loc, 0)
+    assert A.giveNumberOfNonzeros() == 0
+    S = ElementSet(ctx, "lspace", coords, conn, np.zeros(2, np.int32), [[1, 10.0, 0.2, 0, 0, 0, 0, 0]], loc, 0)
+    S.assembleStiffness(A)
+    Ke = S.computeStiffnessMatrix()
+    assert np.isfinite(Ke).all() and np.allclose(Ke, Ke.transpose(0, 2, 1), atol=1e-12 * np.abs(Ke).max())
+    # rigid translation produces no internal forces
+    fe = S.giveInternalForcesVector(np.ones((coords.shape[0], 3)))
+    assert np.abs(fe).max() < 1e-12 * np.abs(Ke).max()
+
+
+def test_device_resident_inputs(ctx):
+    """on_device = 1: torch CUDA tensors are consumed in place (the `value` path of bench.py)."""
+    import torch
+    pb = _random_problem("lspace", 6, 4, 4, seed=11, mat=Material("isole", 1.0e4, 0.3))
+    dom = Domain(ctx, pb)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(a, device=dev)
+    S = ElementSet(ctx, "lspace", t(pb.coords), t(pb.conn), t(pb.elem_mat), pb.matparams(), t(dom.loc), dom.neq)
+    torch.cuda.synchronize()
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(t(dom.loc), dom.neq)
+    S.assembleStiffness(A)
+    B = CudaCSR(ctx)
+    B.buildInternalStructure(dom.loc, dom.neq)
+    dom.elems.assembleStiffness(B)
+    assert np.array_equal(A.structure()[1], B.structure()[1])
+    assert relerr(A.values(), B.values()) < 1e-13
+    b = torch.ones(dom.neq, dtype=torch.float64, device=dev)
+    x = torch.zeros(dom.neq, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    s = CudaCG(ctx).initializeFrom(dict(lstol=1e-10, lsiter=5000, lsprecond=1))
+    assert s.solve(A, b, x) == CR_CONVERGED
+    ctx.sync()
+    xh = np.zeros(dom.neq)
+    s.solve(B, np.ones(dom.neq), xh)
+    assert relerr(x.cpu().numpy(), xh) < 1e-8
+
+
+def test_linearity_and_symmetry_at_scale(ctx):
+    """Size-independent properties on a mesh the oracle would take long for (200k elements):
+    A symmetric (x.Ay == y.Ax), rigid-body translations in the null space of the free-free
+    operator, CG solution satisfies the system."""
+    nx, ny, nz = 128, 40, 40
+    coords, conn = meshgen.hex_beam(nx, ny, nz)
+    fixed, tip = meshgen.cantilever_bcs(coords, float(nx) / ny)
+    mask = np.zeros((coords.shape[0], 3), bool)
+    mask[fixed - 1] = True
+    nodeeq, neq = meshgen.equation_numbers(coords.shape[0], mask)
+    loc = meshgen.location_arrays(conn, nodeeq)
+    S = ElementSet(ctx, "lspace", coords, conn, np.zeros(conn.shape[0], np.int32), [[1, 210e3, 0.3, 0, 0, 0, 0, 0]], loc, neq)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(loc, neq)
+    S.assembleStiffness(A)
+    rp, ci = A.structure()
+    assert rp[-1] == A.giveNumberOfNonzeros() and np.all(np.diff(rp) > 0) and np.diff(rp).max() == 81
+    rows = np.repeat(np.arange(neq), np.diff(rp))
+    assert np.all(ci[1:][rows[1:] == rows[:-1]] > ci[:-1][rows[1:] == rows[:-1]])       # sorted rows
+    rng = np.random.default_rng(4)
+    x, y = rng.normal(size=neq), rng.normal(size=neq)
+    Ax, Ay = A.times(x), A.times(y)
+    assert abs(x @ Ay - y @ Ax) < 1e-10 * abs(x @ Ay)
+    assert relerr(A.times(2.0 * x + y), 2.0 * Ax + Ay) < 1e-13
+    # rigid translation of the whole body: internal forces vanish
+    f = np.zeros(neq)
+    S.assembleInternalForces(np.ones_like(coords), f)
+    assert np.abs(f).max() < 1e-9 * np.abs(A.values()).max()
+    b = rng.normal(size=neq)
+    xs = np.zeros(neq)
+    s = CudaCG(ctx).initializeFrom(dict(lstol=1e-10, lsiter=20000, lsprecond=1))
+    assert s.solve(A, b, xs) == CR_CONVERGED
+    assert np.linalg.norm(A.times(xs) - b) / np.linalg.norm(b) < 2e-10
