@@ -1,0 +1,460 @@
+#!/usr/bin/env python3
+"""bench.py -- elements assembled/s + PCG iterations/s on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1], the synthetic structured 1M-hex LSpace
+isotropic linear-elastic cantilever beam (250 x 64 x 64 = 1,024,000 elements, ~3.17M equations,
+~250M non-zeros) per GPU; with N > 1 the beam is N times longer and element-partitioned into N
+slabs (weak scaling), shared-plane halo exchange and dot-product all-reduce over NCCL.
+
+One "step" = one pass of the hot path: zero the matrix, assemble all element stiffness
+matrices into the CSR matrix (fused LSpace kernel), then `--cg-iters` PCG iterations
+(SpMV + axpy + dot, diagonal preconditioner) on that matrix.
+  value            elements assembled/s, inputs resident in HBM (whole job, all ranks)
+  pcg_iters_per_s  PCG iterations/s in the same step
+  e2e              same two numbers through the host-pointer C ABI: mesh arrays and vectors
+                   start in pinned host memory, H2D/D2H copies inside the timed region
+  roofline         dominant kernel (the CG SpMV) against the measured HBM copy bandwidth
+  cpu_baseline     the unmodified reference (oracle/_ref/oofem_bench) on the box's host cores,
+                   on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------
+
+def slab_problem(nx, ny, nz, rank, nranks):
+    """Local mesh of rank `rank`: slab [rank*nx, (rank+1)*nx] of a beam nranks*nx long.
+    Returns dict(coords, conn, loc, neq, nodeeq, shared planes)."""
+    from oofem_b200 import meshgen
+    h = 1.0 / ny
+    coords, conn = meshgen.hex_beam(nx, ny, nz, nx * h, 1.0, nz * h)
+    coords[:, 0] += rank * nx * h
+    fixed_mask = np.zeros((coords.shape[0], 3), dtype=bool)
+    plane = (ny + 1) * (nz + 1)
+    if rank == 0:
+        fixed_mask[:plane] = True                       # clamp x = 0
+    nodeeq, neq = meshgen.equation_numbers(coords.shape[0], fixed_mask)
+    loc = meshgen.location_arrays(conn, nodeeq)
+    first = nodeeq[:plane].reshape(-1)                  # shared with rank-1
+    last = nodeeq[-plane:].reshape(-1)                  # shared with rank+1
+    return dict(coords=coords, conn=conn, loc=loc, neq=neq, nodeeq=nodeeq, first=first, last=last, plane=plane)
+
+
+def halo_arrays(pb, rank, nranks):
+    neigh, offs, eqs = [], [0], []
+    owned = np.ones(pb["neq"], dtype=np.uint8)
+    if rank > 0:
+        e = pb["first"][pb["first"] > 0] - 1
+        neigh.append(rank - 1)
+        eqs.append(e)
+        offs.append(offs[-1] + e.size)
+        owned[e] = 0                                    # the lower rank owns the shared plane
+    if rank < nranks - 1:
+        e = pb["last"][pb["last"] > 0] - 1
+        neigh.append(rank + 1)
+        eqs.append(e)
+        offs.append(offs[-1] + e.size)
+    eqs = np.concatenate(eqs).astype(np.int32) if eqs else np.zeros(0, np.int32)
+    return np.array(neigh, np.int32), np.array(offs, np.int64), eqs, owned
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ---------------------------------------------------------------------------------------
+
+def reference_sample(dims, cg_iters, repeats, prefer_omp=True):
+    """Time the UNMODIFIED reference (oracle/_ref/oofem_bench[_omp]) on a bounded sample."""
+    from oofem_b200 import meshgen
+    from oofem_b200.inputfile import DirichletBC, Material, NodalLoad, Problem, write_input
+    nx, ny, nz = dims
+    exes = [os.path.join(ROOT, "oracle", "_ref", n) for n in (("oofem_bench_omp",) if prefer_omp else ()) + ("oofem_bench",)]
+    exe = next((e for e in exes if os.path.exists(e)), None)
+    if exe is None:
+        return None
+    h = 1.0 / ny
+    coords, conn = meshgen.hex_beam(nx, ny, nz, nx * h, 1.0, nz * h)
+    fixed, tip = meshgen.cantilever_bcs(coords, nx * h)
+    with tempfile.TemporaryDirectory() as td:
+        pb = Problem(title="bench sample", outfile=os.path.join(td, "s.out"), engng="linearstatic",
+                     params=dict(nsteps=1, lstype=1, smtype=2, lstol=0.5, lsiter=1000, lsprecond=1), coords=coords,
+                     elem_type="lspace", conn=conn, elem_mat=np.zeros(conn.shape[0], np.int32),
+                     materials=[Material("isole", 210e3, 0.3)])
+        pb.ltfs[1] = ("const", 1.0)
+        pb.bcs.append(DirichletBC([1, 2, 3], [0.0, 0.0, 0.0], 1, fixed))
+        pb.loads.append(NodalLoad([3], [-1.0], 1, tip))
+        fn = os.path.join(td, "s.in")
+        write_input(fn, pb)
+        env = dict(os.environ)
+        env.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+        r = subprocess.run([exe, fn, str(cg_iters), str(repeats)], cwd=td, capture_output=True, text=True, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode or not line:
+        return None
+    out = json.loads(line[-1])
+    out["exe"] = os.path.basename(exe)
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    dims = (40, 20, 20)
+    repeats = max(1, min(args.steps, 3))
+    t0 = time.time()
+    res = reference_sample(dims, args.cg_iters, repeats)
+    if res is None:      # reference binary not built here: time the C port of the same algorithm
+        res = oracle_sample(dims, args.cg_iters)
+        kind = "port"
+    else:
+        kind = "reference"
+    ms = (res["t_assemble_s"] + res["t_cg_s"]) * 1e3
+    line = {
+        "impl": "reference", "metric": "elements assembled/s", "value": res["elements_per_s"], "unit": "elements/s",
+        "pcg_iters_per_s": res["cg_iters_per_s"], "n_gpus": args.gpus, "steps": repeats, "warmup": 0,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "synthetic structured 1M-hex LSpace isotropic linear elastic beam, FP64 PCG "
+                               "(BASELINE.json configs[1]); reference arm runs a bounded sample of it",
+                   "sample": f"{dims[0]}x{dims[1]}x{dims[2]} hex = {res['nelem']} elements, neq {res['neq']}, "
+                             f"nnz {res['nnz']}, {args.cg_iters} CG iterations", "cg_iters_per_step": args.cg_iters},
+        "cpu_baseline": {"value": res["elements_per_s"], "unit": "elements/s", "pcg_iters_per_s": res["cg_iters_per_s"],
+                         "cores": res.get("threads", 1), "kind": kind,
+                         "sample": f"{res['nelem']} LSpace elements assembled by EngngModel::assemble into CompCol; "
+                                   f"{args.cg_iters} IML CG iterations at nnz {res['nnz']}"},
+        "e2e": {"value": res["elements_per_s"], "unit": "elements/s", "pcg_iters_per_s": res["cg_iters_per_s"],
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def oracle_sample(dims, cg_iters):
+    from oofem_b200 import meshgen
+    from oracle import oracle as orc
+    nx, ny, nz = dims
+    coords, conn = meshgen.hex_beam(nx, ny, nz)
+    fixed, _ = meshgen.cantilever_bcs(coords, float(nx) / ny)
+    mask = np.zeros((coords.shape[0], 3), bool)
+    mask[fixed - 1] = True
+    nodeeq, neq = meshgen.equation_numbers(coords.shape[0], mask)
+    loc = meshgen.location_arrays(conn, nodeeq)
+    colptr, rowind = orc.compcol_build(loc, neq)
+    mp = np.array([[1, 210e3, 0.3, 0, 0, 0, 0, 0]], dtype=np.float64)
+    t0 = time.time()
+    Ke = orc.batch_stiffness(orc.LSPACE, conn, coords, np.zeros(conn.shape[0], np.int32), mp)
+    val = orc.compcol_assemble(loc, Ke, colptr, rowind)
+    t_asm = time.time() - t0
+    b = np.ones(neq)
+    t0 = time.time()
+    orc.cg(colptr, rowind, val, b, precond=1, max_iter=cg_iters, tol=1e-300)
+    t_cg = time.time() - t0
+    return dict(nelem=conn.shape[0], neq=neq, nnz=int(rowind.size), threads=1, t_assemble_s=t_asm, t_cg_s=t_cg,
+                elements_per_s=conn.shape[0] / t_asm, cg_iters_per_s=cg_iters / t_cg)
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    from oofem_b200 import capi
+    from oofem_b200.capi import check, lib, ptr
+    from oofem_b200.elements import ElementSet
+    from oofem_b200.linsolver import CudaCG
+    from oofem_b200.sparsemtrx import CudaCSR
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    dev = torch.device("cuda", local)
+    nx, ny, nz = args.nx, args.ny, args.nz
+    pb = slab_problem(nx, ny, nz, rank, world)
+    nelem, neq = pb["conn"].shape[0], pb["neq"]
+    matparams = np.array([[capi.MAT_ISOLE, 210e3, 0.3, 0, 0, 0, 0, 0]], dtype=np.float64)
+    matid = np.zeros(nelem, np.int32)
+
+    # ---- resident inputs (value) ---------------------------------------------------
+    t = lambda a: torch.as_tensor(a, device=dev)
+    d_coords, d_conn, d_loc, d_matid = t(pb["coords"]), t(pb["conn"]), t(pb["loc"]), t(matid)
+    torch.cuda.synchronize()
+    S = ElementSet(ctx, "lspace", d_coords, d_conn, d_matid, matparams, d_loc, neq)
+    A = CudaCSR(ctx)
+    t0 = time.time()
+    A.buildInternalStructure(d_loc, neq)
+    ctx.sync()
+    t_structure = time.time() - t0
+    S.bind(A)
+    nnz = A.giveNumberOfNonzeros()
+    comm = None
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            check(lib().ob200_comm_unique_id(raw))
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.to(dev)
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_char * 128).from_buffer_copy(bytes(idbuf.cpu().numpy().tobytes()))
+
+        class _Comm:
+            pass
+        comm = _Comm()
+        comm.h = C.c_void_p()
+        check(lib().ob200_comm_create(ctx.h, world, rank, raw, C.byref(comm.h)))
+        neigh, offs, eqs, owned = halo_arrays(pb, rank, world)
+        check(lib().ob200_comm_set_halo(comm.h, neq, len(neigh), ptr(neigh), ptr(offs), ptr(eqs), ptr(owned)))
+    solver = CudaCG(ctx, comm).initializeFrom(dict(lstol=0.0, lsiter=args.cg_iters, lsprecond=1))
+    b = torch.ones(neq, dtype=torch.float64, device=dev)
+    x = torch.zeros(neq, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def step_resident(ev=None):
+        if ev:
+            ev[0].record(ext)
+        A.zero()
+        S.assembleStiffness(A)
+        if ev:
+            ev[1].record(ext)
+        x.zero_()
+        torch.cuda.current_stream().synchronize()
+        solver.solve(A, b, x)
+        if ev:
+            ev[2].record(ext)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    wall0 = time.time()
+    for k in range(args.steps):
+        step_resident(evs[k])
+    barrier()
+    wall = time.time() - wall0
+    clocks = sampler.stop()
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    launches = ctx.launches - launches0
+    t_asm = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps          # ms
+    t_cg = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    tt = torch.tensor([t_asm, t_cg, t_asm + t_cg], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_asm, t_cg, t_step = [float(v) for v in tt.cpu()]
+
+    # ---- end to end through the host-pointer C ABI ---------------------------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_coords, h_conn, h_loc, h_matid = pin(pb["coords"]), pin(pb["conn"]), pin(pb["loc"]), pin(matid)
+    h_b, h_x = pin(np.ones(neq)), pin(np.zeros(neq))
+    h2d_asm = h_coords.nbytes + h_conn.nbytes + h_loc.nbytes + h_matid.nbytes + matparams.nbytes
+    h2d_cg, d2h_cg = h_b.nbytes + h_x.nbytes, h_x.nbytes
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        S2 = ElementSet(ctx, "lspace", h_coords, h_conn, h_matid, matparams, h_loc, neq)   # H2D of the mesh
+        A.zero()
+        S2.assembleStiffness(A)                                                           # slot map + fused assembly
+        ctx.sync()
+        t1 = time.perf_counter()
+        h_x[:] = 0.0
+        solver.solve(A, h_b, h_x)                                                          # H2D b,x ; D2H x
+        t2 = time.perf_counter()
+        S2.close()
+        return t1 - t0, t2 - t1
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    ts = [step_e2e() for _ in range(e2e_steps)]
+    barrier()
+    e_asm = sum(a for a, _ in ts) / e2e_steps
+    e_cg = sum(c for _, c in ts) / e2e_steps
+    te = torch.tensor([e_asm, e_cg], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_asm, e_cg = [float(v) for v in te.cpu()]
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ---------------------------------------------
+    peak, peak_src = load_peaks()
+    spmv_name = "cg_spmv_kernel< true >" if world == 1 else "cg_spmv_kernel< false >"
+    asm_name = "lspace_stiffness_kernel< OUT_CSR >"
+    ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
+    ms_asmk, n_asmk = prof.get(asm_name, (0.0, 0))
+    # algorithmic bytes: SpMV reads val (8 B) + colind (4 B) per non-zero, and per
+    # row rowptr (4 B), the operand entry once (8 B), writes the result (8 B)
+    spmv_bytes = 12.0 * nnz + 20.0 * neq
+    spmv_dur = ms_spmv / max(n_spmv, 1) * 1e-3
+    spmv_gbs = spmv_bytes / spmv_dur / 1e9 if spmv_dur > 0 else 0.0
+    # assembly: conn (32 B) + matid (4 B) + slot map (576 x 4 B) per element, coordinates once per node
+    # (24 B), every matrix value written once (8 B per non-zero)
+    asm_bytes = nelem * (32.0 + 4.0 + 2304.0) + pb["coords"].shape[0] * 24.0 + 8.0 * nnz
+    asm_dur = ms_asmk / max(n_asmk, 1) * 1e-3
+    asm_gbs = asm_bytes / asm_dur / 1e9 if asm_dur > 0 else 0.0
+    kernel_share = {k: round(v[0] / (t_step * args.steps) , 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = reference_sample((40, 20, 20), 20, 1)
+        kind = "reference"
+        if cpu is None:
+            cpu = oracle_sample((40, 20, 20), 20)
+            kind = "port"
+    total_elems = nelem * world
+    line = {
+        "metric": "elements assembled/s", "value": total_elems / (t_asm * 1e-3), "unit": "elements/s",
+        "pcg_iters_per_s": args.cg_iters / (t_cg * 1e-3),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
+        "ms_assembly": t_asm, "ms_pcg": t_cg,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic structured {nx}x{ny}x{nz} = {nelem} hex LSpace isotropic linear elastic "
+                               f"cantilever per GPU, FP64 PCG (BASELINE.json configs[1])",
+                   "nelem_per_gpu": nelem, "neq_per_gpu": neq, "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
+                   "precond": "diag", "partition": f"{world} x-slabs, shared-plane halo" if world > 1 else "none",
+                   "l2": "inputs larger than L2 (val+colind ~3 GB per pass vs 126 MB L2), no flush needed",
+                   "structure_build_s": round(t_structure, 4)},
+        "roofline": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": spmv_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_dur * 1e3, "launches": n_spmv},
+        "roofline_assembly": {"kernel": asm_name, "bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": asm_gbs / peak, "traffic": None, "algorithmic_bytes_per_launch": asm_bytes,
+                              "avg_launch_ms": asm_dur * 1e3, "launches": n_asmk,
+                              "note": "FP64-pipe bound rather than HBM bound, see DESIGN.md"},
+        "kernel_time_share": kernel_share,
+        "e2e": {"value": total_elems / e_asm, "unit": "elements/s", "pcg_iters_per_s": args.cg_iters / e_cg,
+                "h2d_bytes_per_step": int(h2d_asm + h2d_cg), "d2h_bytes_per_step": int(d2h_cg),
+                "ms_assembly": e_asm * 1e3, "ms_pcg": e_cg * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {"value": cpu["elements_per_s"], "unit": "elements/s", "pcg_iters_per_s": cpu["cg_iters_per_s"],
+                                "cores": cpu.get("threads", 1), "kind": kind,
+                                "sample": f"{cpu['nelem']} LSpace elements (40x20x20 sample of the same beam) assembled by the "
+                                          f"reference's EngngModel::assemble into CompCol; 20 IML CG iterations at nnz {cpu['nnz']}"}
+    print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=250)
+    ap.add_argument("--ny", type=int, default=64)
+    ap.add_argument("--nz", type=int, default=64)
+    ap.add_argument("--cg-iters", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -64,6 +64,11 @@ int  ob200_context_sync(ob200_context *ctx);
 void *ob200_context_stream(ob200_context *ctx);
 /* number of kernels launched through this context so far (bench.py's gpu_launches) */
 int64_t ob200_context_launch_count(ob200_context *ctx);
+/* per-kernel CUDA-event timing on the launching stream (bench.py's roofline): enable, run,
+ * then read "kernel-name<TAB>total-ms<TAB>launches" lines */
+int  ob200_context_set_profiling(ob200_context *ctx, int enable);
+int  ob200_context_profile_reset(ob200_context *ctx);
+int  ob200_context_profile_report(ob200_context *ctx, char *buf, int64_t buflen);
 /* device memory helpers so that callers without a CUDA runtime binding can keep data resident */
 int  ob200_malloc(ob200_context *ctx, int64_t bytes, void **dptr);
 int  ob200_free(ob200_context *ctx, void *dptr);
@@ -124,8 +129,12 @@ int  ob200_elemset_internal_forces(ob200_elemset *S, const double *u, double *fe
 int  ob200_elemset_bind(ob200_elemset *S, ob200_csr *A);
 /* fused: A += sum_e Ke scattered through loc (EngngModel::assemble with TangentAssembler) */
 int  ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A);
-/* fused: f[neq] += sum_e fe scattered through loc (assembleVector with InternalForceAssembler) */
-int  ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, double *f, int on_device);
+/* fused: f[neq] += sum_e fe scattered through loc (assembleVector with InternalForceAssembler).
+ * ebe_norm2 (HOST pointer, 3 doubles, may be NULL) receives the element-by-element squared
+ * norms per dof id u,v,w -- the eNorms of EngngModel::assembleVector (engngm.C:1108-1133)
+ * that NRSolver::checkConvergence scales the force error with (nrsolver.C:752-760). */
+int  ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, double *f,
+                                            double *ebe_norm2, int on_device);
 /* f[neq] += sum_e Ke * du_e for nodal increments du [nnode][3]
  * (StaticStructural::assembleExtrapolatedForces, staticstructural.C:255) */
 int  ob200_elemset_assemble_extrapolated_forces(ob200_elemset *S, const double *du, double *f, int on_device);

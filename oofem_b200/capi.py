@@ -32,6 +32,9 @@ SYMBOLS = {
     "ob200_context_sync": (_int, [_vp]),
     "ob200_context_stream": (_vp, [_vp]),
     "ob200_context_launch_count": (_i64, [_vp]),
+    "ob200_context_set_profiling": (_int, [_vp, _int]),
+    "ob200_context_profile_reset": (_int, [_vp]),
+    "ob200_context_profile_report": (_int, [_vp, C.c_char_p, _i64]),
     "ob200_malloc": (_int, [_vp, _i64, _pp]),
     "ob200_free": (_int, [_vp, _vp]),
     "ob200_memcpy_h2d": (_int, [_vp, _vp, _vp, _i64]),
@@ -60,7 +63,7 @@ SYMBOLS = {
     "ob200_elemset_internal_forces": (_int, [_vp, _vp, _vp, _vp, _vp, _int]),
     "ob200_elemset_bind": (_int, [_vp, _vp]),
     "ob200_elemset_assemble_stiffness": (_int, [_vp, _vp]),
-    "ob200_elemset_assemble_internal_forces": (_int, [_vp, _vp, _vp, _int]),
+    "ob200_elemset_assemble_internal_forces": (_int, [_vp, _vp, _vp, _vp, _int]),
     "ob200_elemset_assemble_extrapolated_forces": (_int, [_vp, _vp, _vp, _int]),
     "ob200_elemset_commit": (_int, [_vp]),
     "ob200_elemset_get_state": (_int, [_vp, _vp, _int]),
@@ -145,6 +148,22 @@ class Context:
 
     def flush_l2(self):
         check(lib().ob200_flush_l2(self.h))
+
+    def set_profiling(self, enable: bool):
+        check(lib().ob200_context_set_profiling(self.h, 1 if enable else 0))
+
+    def profile_reset(self):
+        check(lib().ob200_context_profile_reset(self.h))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (total ms, launches)} measured with CUDA events around every launch."""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().ob200_context_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split("\t")
+            out[name] = (float(ms), int(n))
+        return out
 
     def close(self):
         if self.h:

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/oofem_b200.h"
@@ -76,12 +77,30 @@ struct DevBuf {
 
 } // namespace ob200
 
+struct ob200_prof_rec {
+    const char *name;
+    cudaEvent_t start, stop;
+};
+
 struct ob200_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop;
     ob200::LaunchShape shape;
     int64_t launches = 0;
+    // optional per-kernel CUDA-event timing (bench.py roofline): every launch is bracketed by
+    // two events on the launching stream; ob200_context_profile_collect folds them into totals
+    bool profiling = false;
+    std::vector< ob200_prof_rec > prof_pending;
+    std::vector< cudaEvent_t > prof_pool;
+    std::map< std::string, std::pair< double, int64_t > > prof_total;
+    cudaEvent_t prof_event()
+    {
+        cudaEvent_t e;
+        if ( !prof_pool.empty() ) { e = prof_pool.back(); prof_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
     // L2 flush scratch
     ob200::DevBuf< char > flush;
     // reduction scratch (partials) and small device scalars, used by CG
@@ -90,7 +109,17 @@ struct ob200_context {
 
 #define OB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
     do {                                                                                 \
+        ob200_prof_rec pr__ = { #kernel, nullptr, nullptr };                             \
+        if ( ( ctx )->profiling ) {                                                      \
+            pr__.start = ( ctx )->prof_event();                                          \
+            pr__.stop = ( ctx )->prof_event();                                           \
+            cudaEventRecord(pr__.start, ( ctx )->stream);                                \
+        }                                                                                \
         kernel<<< ( grid ), ( block ), ( smem ), ( ctx )->stream >>>(__VA_ARGS__);       \
+        if ( ( ctx )->profiling ) {                                                      \
+            cudaEventRecord(pr__.stop, ( ctx )->stream);                                 \
+            ( ctx )->prof_pending.push_back(pr__);                                       \
+        }                                                                                \
         ( ctx )->launches++;                                                             \
         OB_CUDA( cudaGetLastError() );                                                   \
     } while ( 0 )

@@ -1,6 +1,7 @@
 // Context, error reporting and raw device-memory helpers of the C ABI.
 #include "common.cuh"
 #include <stdarg.h>
+#include <string.h>
 
 namespace ob200 {
 static thread_local char g_err[1024] = "";
@@ -72,6 +73,52 @@ int ob200_context_sync(ob200_context *ctx)
 
 void *ob200_context_stream(ob200_context *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
 int64_t ob200_context_launch_count(ob200_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int ob200_context_set_profiling(ob200_context *ctx, int enable)
+{
+    OB_REQUIRE(ctx, OB200_EINVAL, "set_profiling: null context");
+    ctx->profiling = enable != 0;
+    return OB200_OK;
+}
+
+static int profile_fold(ob200_context *ctx)
+{
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    for ( auto &r : ctx->prof_pending ) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        auto &t = ctx->prof_total[r.name];
+        t.first += ms;
+        t.second += 1;
+        ctx->prof_pool.push_back(r.start);
+        ctx->prof_pool.push_back(r.stop);
+    }
+    ctx->prof_pending.clear();
+    return OB200_OK;
+}
+
+int ob200_context_profile_reset(ob200_context *ctx)
+{
+    OB_REQUIRE(ctx, OB200_EINVAL, "profile_reset: null context");
+    OB_CHECK( profile_fold(ctx) );
+    ctx->prof_total.clear();
+    return OB200_OK;
+}
+
+int ob200_context_profile_report(ob200_context *ctx, char *buf, int64_t buflen)
+{
+    OB_REQUIRE(ctx && buf && buflen > 0, OB200_EINVAL, "profile_report: bad argument");
+    OB_CHECK( profile_fold(ctx) );
+    std::string out;
+    for ( auto &kv : ctx->prof_total ) {
+        char line[512];
+        snprintf(line, sizeof( line ), "%s\t%.6f\t%lld\n", kv.first.c_str(), kv.second.first, (long long) kv.second.second);
+        out += line;
+    }
+    OB_REQUIRE((int64_t) out.size() < buflen, OB200_EINVAL, "profile_report: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return OB200_OK;
+}
 
 int ob200_malloc(ob200_context *ctx, int64_t bytes, void **dptr)
 {

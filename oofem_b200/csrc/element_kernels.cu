@@ -113,11 +113,13 @@ lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *
 __global__ void __launch_bounds__(kHexWarps * 32)
 lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
                               double *__restrict__ fglob, double *__restrict__ gp_strain,
-                              double *__restrict__ gp_stress, int64_t e_begin, int64_t e_end)
+                              double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
+                              int64_t e_begin, int64_t e_end)
 {
     __shared__ HexShared sh[kHexWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     HexShared &s = sh[wid];
+    double ebe = 0.0;      // sum of f^2 of this lane's dof id over the elements of this warp
     const int64_t stride = (int64_t) gridDim.x * kHexWarps;
     for ( int64_t e = e_begin + (int64_t) blockIdx.x * kHexWarps + wid; e < e_end; e += stride ) {
         if ( lane < 24 ) {
@@ -160,6 +162,7 @@ lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, doubl
                 force_node(fk, s.g[gp][k], s.sig[gp], s.dV[gp]);
                 f += ( c == 0 ? fk[0] : ( c == 1 ? fk[1] : fk[2] ) );
             }
+            ebe += f * f;
             if ( fe ) fe[e * 24 + lane] = f;
             if ( fglob ) {
                 int32_t r = S.loc[e * 24 + lane];
@@ -167,6 +170,15 @@ lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, doubl
             }
         }
         __syncwarp();
+    }
+    if ( ebe_norm2 ) {     // element-by-element norm per dof id (EngngModel::assembleVector eNorms, engngm.C:1108-1133)
+#pragma unroll
+        for ( int c = 0; c < 3; c++ ) {
+            double v = ( lane < 24 && lane % 3 == c ) ? ebe : 0.0;
+#pragma unroll
+            for ( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ( lane == 0 && v != 0.0 ) atomicAdd(ebe_norm2 + c, v);
+        }
     }
 }
 
@@ -240,8 +252,10 @@ ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t
 __global__ void __launch_bounds__(128)
 ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
                                 double *__restrict__ fglob, double *__restrict__ gp_strain,
-                                double *__restrict__ gp_stress, int64_t e_begin, int64_t e_end)
+                                double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
+                                int64_t e_begin, int64_t e_end)
 {
+    double ebe[3] = { 0.0, 0.0, 0.0 };
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for ( int64_t e = e_begin + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += stride ) {
         double g[4][3];
@@ -273,12 +287,22 @@ ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, dou
             force_node(fk, g[a], sig, dV);
 #pragma unroll
             for ( int i = 0; i < 3; i++ ) {
+                ebe[i] += fk[i] * fk[i];
                 if ( fe ) fe[e * 12 + 3 * a + i] = fk[i];
                 if ( fglob ) {
                     int32_t r = S.loc[e * 12 + 3 * a + i];
                     if ( r > 0 ) atomicAdd(fglob + r - 1, fk[i]);
                 }
             }
+        }
+    }
+    if ( ebe_norm2 ) {
+#pragma unroll
+        for ( int c = 0; c < 3; c++ ) {
+            double v = ebe[c];
+#pragma unroll
+            for ( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ( ( threadIdx.x & 31 ) == 0 && v != 0.0 ) atomicAdd(ebe_norm2 + c, v);
         }
     }
 }
@@ -342,17 +366,18 @@ static int launch_stiffness(ob200_elemset *S, int mode, double *out, const int32
     return OB200_OK;
 }
 
-static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe, double *fglob, double *eps, double *sig)
+static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe, double *fglob, double *eps, double *sig,
+                                  double *ebe = nullptr)
 {
     ob200_context *ctx = S->ctx;
     ElemSetView v = S->view();
     if ( S->nelem == 0 ) return OB200_OK;
     if ( S->etype == OB200_LSPACE ) {
         int grid = ctx->shape.grid(S->nelem * 32, kHexWarps * 32, 4);
-        OB_LAUNCH(ctx, lspace_internal_forces_kernel, grid, kHexWarps * 32, 0, v, u, fe, fglob, eps, sig, 0, S->nelem);
+        OB_LAUNCH(ctx, lspace_internal_forces_kernel, grid, kHexWarps * 32, 0, v, u, fe, fglob, eps, sig, ebe, 0, S->nelem);
     } else {
         int grid = ctx->shape.grid(S->nelem, 128, 8);
-        OB_LAUNCH(ctx, ltrspace_internal_forces_kernel, grid, 128, 0, v, u, fe, fglob, eps, sig, 0, S->nelem);
+        OB_LAUNCH(ctx, ltrspace_internal_forces_kernel, grid, 128, 0, v, u, fe, fglob, eps, sig, ebe, 0, S->nelem);
     }
     return OB200_OK;
 }
@@ -489,14 +514,23 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
     return OB200_OK;
 }
 
-int ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, double *f, int on_device)
+int ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, double *f, double *ebe_norm2, int on_device)
 {
     OB_REQUIRE(S && u && f, OB200_EINVAL, "elemset_assemble_internal_forces: null argument");
     Staged< double > du;
     StagedOut< double > of;
     OB_CHECK( du.stage(S->ctx, u, S->nnode * 3, on_device) );
     OB_CHECK( of.stage(S->ctx, f, S->neq_hint(), on_device, true) );
-    OB_CHECK( launch_internal_forces(S, du.d, nullptr, of.d, nullptr, nullptr) );
+    DevBuf< double > ebe;
+    if ( ebe_norm2 ) {
+        OB_CHECK( ebe.alloc(3) );
+        OB_CUDA( cudaMemsetAsync(ebe.p, 0, sizeof( double ) * 3, S->ctx->stream) );
+    }
+    OB_CHECK( launch_internal_forces(S, du.d, nullptr, of.d, nullptr, nullptr, ebe.p) );
+    if ( ebe_norm2 ) {      // always returned to the host: three scalars for the convergence test
+        OB_CUDA( cudaMemcpyAsync(ebe_norm2, ebe.p, sizeof( double ) * 3, cudaMemcpyDeviceToHost, S->ctx->stream) );
+        OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
+    }
     return of.finish(S->ctx);
 }
 

@@ -72,11 +72,12 @@ class ElementSet:
         """A += sum_e Ke (EngngModel::assemble with TangentAssembler), fused on the device."""
         check(lib().ob200_elemset_assemble_stiffness(self.h, A.h))
 
-    def assembleInternalForces(self, u, f):
-        """f[neq] += sum_e fe (EngngModel::assembleVector with InternalForceAssembler)."""
+    def assembleInternalForces(self, u, f, eNorms=None):
+        """f[neq] += sum_e fe (EngngModel::assembleVector with InternalForceAssembler).
+        eNorms: optional numpy float64[3] receiving the element-by-element squared norms per dof id."""
         if isinstance(u, np.ndarray):
             u = np.ascontiguousarray(u, dtype=np.float64)
-        check(lib().ob200_elemset_assemble_internal_forces(self.h, ptr(u), ptr(f), on_device(u)))
+        check(lib().ob200_elemset_assemble_internal_forces(self.h, ptr(u), ptr(f), ptr(eNorms), on_device(u)))
         return f
 
     def assembleExtrapolatedForces(self, du, f):

@@ -103,8 +103,22 @@ class StaticStructural:
 
     def internal_forces(self, t):
         f = np.zeros(self.domain.neq)
-        self.domain.elems.assembleInternalForces(self.domain.full_u(self.solution, t), f)
+        self.internalForcesEBENorm = np.zeros(3)
+        self.domain.elems.assembleInternalForces(self.domain.full_u(self.solution, t), f, self.internalForcesEBENorm)
         return f
+
+    def force_error(self, rhs, fext):
+        """NRSolver::checkConvergence (nrsolver.C:594-760): per dof id group (D_u, D_v, D_w)
+        forceErr = sqrt( sum rhs^2 / ( sum RT^2 + internalForcesEBENorm ) ); the largest governs."""
+        d = self.domain
+        dofid = np.nonzero(d.free)[1]              # dof id of every equation, in equation order
+        err = 0.0
+        for g in range(3):
+            m = dofid == g
+            num = float(np.sum(rhs[m] ** 2))
+            den = float(np.sum(fext[m] ** 2)) + float(self.internalForcesEBENorm[g])
+            err = max(err, np.sqrt(num / den) if den >= 1e-6 else np.sqrt(num))     # nrsolver_ERROR_NORM_SMALL_NUM
+        return err
 
     def solveYourselfAt(self, step: int):
         d, pb = self.domain, self.pb
@@ -124,10 +138,8 @@ class StaticStructural:
         while True:
             fint = self.internal_forces(t)
             rhs = fext - fint
-            # relative force error against the larger of external / internal force norms
-            den = max(np.linalg.norm(fext), np.linalg.norm(fint), 1e-300)
-            err = np.linalg.norm(rhs) / den
-            if err < self.rtolf and nite > 0:
+            err = self.force_error(rhs, fext)
+            if err <= self.rtolf and ( nite > 0 or err == 0.0 ):
                 break
             if nite >= self.nsmax:
                 raise capi.OofemB200Error(capi.EINVAL, "Maximum number of iterations reached without convergence")

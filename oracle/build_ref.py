@@ -131,15 +131,21 @@ def main():
     print("built" if r.returncode == 0 else "LINK FAILED", exe)
     if r.returncode:
         return r.returncode
-    # full-precision dump driver: our own main() over the same unmodified reference objects
+    # our own drivers (main() only) over the same unmodified reference objects:
+    # full-precision dump (fixtures) and the timing harness of the reference arm
+    lib_objs = [o for o in objs if not o.endswith("src_main_main.C.o")]
+    drivers = [("ref_bench.cpp", "oofem_bench_omp" if a.openmp else "oofem_bench")]
     if not a.openmp:
-        dump = os.path.join(OUT, "oofem_dump")
-        lib_objs = [o for o in objs if not o.endswith("src_main_main.C.o")]
-        r = subprocess.run(["g++", "-O2", "-std=c++17", "-w", os.path.join(HERE, "ref_dump.cpp"), "-o", dump]
+        drivers.append(("ref_dump.cpp", "oofem_dump"))
+    for src, exe_name in drivers:
+        exe = os.path.join(OUT, exe_name)
+        r = subprocess.run(["g++", "-O2", "-std=c++17", "-w", os.path.join(HERE, src), "-o", exe]
                            + flags + incs + lib_objs + ["-ldl", "-lpthread"], capture_output=True, text=True)
         print(r.stderr[-6000:])
-        print("built" if r.returncode == 0 else "LINK FAILED", dump)
-    return r.returncode
+        print("built" if r.returncode == 0 else "LINK FAILED", exe)
+        if r.returncode:
+            return r.returncode
+    return 0
 
 
 if __name__ == "__main__":

@@ -217,11 +217,23 @@ def solve_nonlinear_static(pb, rtol=1e-10, max_newton=50, lin_tol=1e-13, lin_ite
             fex = assemble_vector(md.loc, np.einsum("eij,ej->ei", Ke, due), md.neq)
             dx, flag, n, res = cg(md.colptr, md.rowind, val, -fex, precond=1, max_iter=lin_iter, tol=lin_tol)
             x = x + dx
+        dofid = np.nonzero(md.nodeeq > 0)[1]
         for it in range(max_newton):
-            fint = md.internal_forces(md.full_u(x, t))
+            u_nodes = md.full_u(x, t)
+            ue = u_nodes[pb.conn - 1].reshape(pb.conn.shape[0], -1)
+            fe = batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, ue, md.state)
+            fint = assemble_vector(md.loc, fe, md.neq)
             r = fext - fint
-            den = max(np.linalg.norm(fext), np.linalg.norm(fint), 1e-300)
-            if np.linalg.norm(r) / den < rtol and it > 0:
+            # NRSolver::checkConvergence (src/core/nrsolver.C:752-760): per dof id,
+            # sqrt( sum rhs^2 / ( sum RT^2 + element-by-element norm of the internal forces ) )
+            ebe = (fe.reshape(fe.shape[0], -1, 3) ** 2).sum(axis=(0, 1))
+            err = 0.0
+            for g in range(3):
+                m = dofid == g
+                den = float(np.sum(fext[m] ** 2)) + float(ebe[g])
+                num = float(np.sum(r[m] ** 2))
+                err = max(err, np.sqrt(num / den) if den >= 1e-6 else np.sqrt(num))
+            if err <= rtol and it > 0:
                 break
             if it > 0:
                 val = md.stiffness()          # manrmsteps 1: refresh every iteration (nrsolver.C:293-298)
