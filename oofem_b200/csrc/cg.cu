@@ -15,14 +15,18 @@
 namespace ob200 {
 
 int spmv(ob200_csr *A, const double *x, double *y);
+int spmv_fused_dot(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done);
 
 struct CgScalars {
     double normb, rho, rho_1, alpha, beta, resid;
     int iters, done;
+    unsigned int ticket;
+    int pad;
 };
 
 constexpr int kRedMax = 3;            // simultaneous reductions
 constexpr int kCgThreads = 256;
+constexpr int kCgMaxBlocks = 2048;    // upper bound on the partial sums of one reduction
 
 __device__ __forceinline__ double warp_sum(double s)
 {
@@ -44,6 +48,62 @@ __device__ __forceinline__ double block_sum(double s, double *scratch /* [32] */
         s = warp_sum(s);
     }
     return s;
+}
+
+// "last block done": true in every thread of the CTA that arrives last at the ticket.  The last
+// CTA then sums the per-block partials in a fixed order -- deterministic, and no extra launch.
+__device__ __forceinline__ bool last_block(unsigned int *ticket)
+{
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = ( t == gridDim.x - 1 );
+        if ( is_last ) *ticket = 0;
+    }
+    __syncthreads();
+    return is_last != 0;
+}
+
+__device__ __forceinline__ double sum_partials(const double *partials, int P, double *scratch)
+{
+    double s = 0.0;
+    for ( int i = threadIdx.x; i < P; i += blockDim.x ) s += __ldcg(partials + i);
+    return block_sum(s, scratch);
+}
+
+// the scalar recurrences of iml/cg.h; one thread
+// stage 0 (init):  red = {b.b, r.r, r.z};  stage 1 (after SpMV): red = {p.q};
+// stage 2 (after x/r update of iteration `iter`): red = {r.r, r.z}
+__device__ __forceinline__ void cg_scalars(int stage, int iter, double tol, const double *red, CgScalars *S)
+{
+    if ( stage == 1 ) {
+        S->alpha = S->rho / red[0];                       // alpha = rho / dot(p, q)     (cg.h:54)
+        return;
+    }
+    double rr, rz;
+    if ( stage == 0 ) {
+        double normb = sqrt(red[0]);                      // Real normb = norm(b)        (cg.h:31)
+        if ( normb == 0.0 ) normb = 1;                    //                              (cg.h:34-35)
+        S->normb = normb;
+        rr = red[1];
+        rz = red[2];
+    } else {
+        rr = red[0];
+        rz = red[1];
+    }
+    double resid = sqrt(rr) / S->normb;
+    S->resid = resid;
+    if ( resid <= tol ) {                                 // (cg.h:37-41, 60-64)
+        S->done = 1;
+        S->iters = iter;
+        return;
+    }
+    S->rho_1 = S->rho;                                    // rho_1 = rho                  (cg.h:66)
+    S->rho = rz;                                          // rho = dot(r, z)              (cg.h:47)
+    S->beta = S->rho / S->rho_1;                          // beta = rho / rho_1           (cg.h:51)
+    S->iters = iter;
 }
 
 // DiagPreconditioner::init (diagpre.C:41-58): diag = 1 / A(i,i); zero diagonal is an error
@@ -93,41 +153,13 @@ __global__ void diag_invert_kernel(int32_t neq, double *__restrict__ diag, int *
     }
 }
 
-// q = A p (warp per row) with the partial sums of p.q fused in (cg.h:53-54).
-// FUSE_DOT = false: plain product (distributed path adds the halo before the dot).
-template< bool FUSE_DOT >
-__global__ void __launch_bounds__(kCgThreads)
-cg_spmv_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-               const double *__restrict__ val, const double *__restrict__ p, double *__restrict__ q,
-               double *__restrict__ partials, const CgScalars *__restrict__ S)
-{
-    __shared__ double scratch[32];
-    if ( S->done ) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
-    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
-    double pq = 0.0;
-    for ( int64_t row = warp0; row < neq; row += nwarps ) {
-        const int b = rowptr[row], e = rowptr[row + 1];
-        double s = 0.0;
-        for ( int t = b + lane; t < e; t += 32 ) s += val[t] * p[colind[t]];
-        s = warp_sum(s);
-        if ( lane == 0 ) {
-            q[row] = s;
-            if ( FUSE_DOT ) pq += s * p[row];
-        }
-    }
-    if ( FUSE_DOT ) {
-        pq = block_sum(pq, scratch);
-        if ( threadIdx.x == 0 ) partials[blockIdx.x] = pq;
-    }
-}
-
 // r = b - q (q = A x already, halo-summed), partials of b.b, r.r, r.z with z = M^-1 r   (cg.h:32-33)
+// FINAL: the last CTA also reduces the partials and runs the stage-0 scalar update.
+template< bool FINAL >
 __global__ void __launch_bounds__(kCgThreads)
 cg_init_kernel(int32_t neq, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
                const double *__restrict__ diag, const unsigned char *__restrict__ owned,
-               double *__restrict__ partials, int P)
+               double *__restrict__ partials, int P, double *__restrict__ red, double tol, CgScalars *S)
 {
     __shared__ double scratch[32];
     double bb = 0.0, rr = 0.0, rz = 0.0;
@@ -147,6 +179,15 @@ cg_init_kernel(int32_t neq, const double *__restrict__ b, const double *__restri
     if ( threadIdx.x == 0 ) partials[P + blockIdx.x] = rr;
     rz = block_sum(rz, scratch);
     if ( threadIdx.x == 0 ) partials[2 * P + blockIdx.x] = rz;
+    if ( last_block(&S->ticket) ) {
+        double s0 = sum_partials(partials, gridDim.x, scratch);
+        double s1 = sum_partials(partials + P, gridDim.x, scratch);
+        double s2 = sum_partials(partials + 2 * P, gridDim.x, scratch);
+        if ( threadIdx.x == 0 ) {
+            red[0] = s0; red[1] = s1; red[2] = s2;
+            if ( FINAL ) cg_scalars(0, 0, tol, red, S);
+        }
+    }
 }
 
 // p = z (first iteration) or p = z + beta p, z = M.solve(r)      (cg.h:45-52, diagpre.C:61-68)
@@ -163,12 +204,28 @@ cg_update_p_kernel(int32_t neq, const double *__restrict__ r, const double *__re
     }
 }
 
+// after the SpMV: red[0] = p.q from the per-CTA partials of the SpMV kernel; FINAL: alpha = rho / p.q
+template< bool FINAL >
+__global__ void __launch_bounds__(kCgThreads)
+cg_pq_kernel(const double *__restrict__ partials, int P, double *__restrict__ red, CgScalars *S)
+{
+    __shared__ double scratch[32];
+    if ( S->done ) return;
+    double s = sum_partials(partials, P, scratch);
+    if ( threadIdx.x == 0 ) {
+        red[0] = s;
+        if ( FINAL ) cg_scalars(1, 0, 0.0, red, S);
+    }
+}
+
 // x += alpha p; r -= alpha q; partials of r.r and r.z for the next test / rho       (cg.h:56-58)
+// FINAL: the last CTA reduces them and runs the convergence test + rho/beta recurrences.
+template< bool FINAL >
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(int32_t neq, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                     const double *__restrict__ q, const double *__restrict__ diag,
                     const unsigned char *__restrict__ owned, double *__restrict__ partials, int P,
-                    const CgScalars *__restrict__ S)
+                    double *__restrict__ red, int iter, double tol, CgScalars *S)
 {
     __shared__ double scratch[32];
     if ( S->done ) return;
@@ -188,12 +245,20 @@ cg_update_xr_kernel(int32_t neq, double *__restrict__ x, double *__restrict__ r,
     if ( threadIdx.x == 0 ) partials[blockIdx.x] = rr;
     rz = block_sum(rz, scratch);
     if ( threadIdx.x == 0 ) partials[P + blockIdx.x] = rz;
+    if ( last_block(&S->ticket) ) {
+        double s0 = sum_partials(partials, gridDim.x, scratch);
+        double s1 = sum_partials(partials + P, gridDim.x, scratch);
+        if ( threadIdx.x == 0 ) {
+            red[0] = s0; red[1] = s1;
+            if ( FINAL ) cg_scalars(2, iter, tol, red, S);
+        }
+    }
 }
 
-// masked dot product partials (distributed path: p.q after the halo sum)
+// masked dot product (distributed path: p.q after the halo sum); last CTA leaves the sum in red[0]
 __global__ void __launch_bounds__(kCgThreads)
 cg_dot_kernel(int32_t neq, const double *__restrict__ a, const double *__restrict__ b,
-              const unsigned char *__restrict__ owned, double *__restrict__ partials, const CgScalars *__restrict__ S)
+              const unsigned char *__restrict__ owned, double *__restrict__ partials, double *__restrict__ red, CgScalars *S)
 {
     __shared__ double scratch[32];
     if ( S->done ) return;
@@ -203,53 +268,17 @@ cg_dot_kernel(int32_t neq, const double *__restrict__ a, const double *__restric
         if ( !owned || owned[i] ) s += a[i] * b[i];
     s = block_sum(s, scratch);
     if ( threadIdx.x == 0 ) partials[blockIdx.x] = s;
-}
-
-// second reduction stage: red[k] = sum_b partials[k*P + b], fixed order
-__global__ void __launch_bounds__(kCgThreads)
-cg_reduce_kernel(const double *__restrict__ partials, int P, int nred, double *__restrict__ red, const CgScalars *__restrict__ S)
-{
-    __shared__ double scratch[32];
-    if ( S->done ) return;
-    for ( int k = 0; k < nred; k++ ) {
-        double s = 0.0;
-        for ( int i = threadIdx.x; i < P; i += blockDim.x ) s += partials[k * P + i];
-        s = block_sum(s, scratch);
-        if ( threadIdx.x == 0 ) red[k] = s;
+    if ( last_block(&S->ticket) ) {
+        double t = sum_partials(partials, gridDim.x, scratch);
+        if ( threadIdx.x == 0 ) red[0] = t;
     }
 }
 
-// stage 0 (init):  red = {b.b, r.r, r.z};  stage 1 (after SpMV): red = {p.q};
-// stage 2 (after x/r update of iteration `iter`): red = {r.r, r.z}
+// distributed path: scalar update after the all-reduce of red[]
 __global__ void cg_scalars_kernel(int stage, int iter, double tol, const double *__restrict__ red, CgScalars *S)
 {
     if ( S->done ) return;
-    if ( stage == 1 ) {
-        S->alpha = S->rho / red[0];                       // alpha = rho / dot(p, q)     (cg.h:54)
-        return;
-    }
-    double rr, rz;
-    if ( stage == 0 ) {
-        double normb = sqrt(red[0]);                      // Real normb = norm(b)        (cg.h:31)
-        if ( normb == 0.0 ) normb = 1;                    //                              (cg.h:34-35)
-        S->normb = normb;
-        rr = red[1];
-        rz = red[2];
-    } else {
-        rr = red[0];
-        rz = red[1];
-    }
-    double resid = sqrt(rr) / S->normb;
-    S->resid = resid;
-    if ( resid <= tol ) {                                 // (cg.h:37-41, 60-64)
-        S->done = 1;
-        S->iters = iter;
-        return;
-    }
-    S->rho_1 = S->rho;                                    // rho_1 = rho                  (cg.h:66)
-    S->rho = rz;                                          // rho = dot(r, z)              (cg.h:47)
-    S->beta = S->rho / S->rho_1;                          // beta = rho / rho_1           (cg.h:51)
-    S->iters = iter;
+    cg_scalars(stage, iter, tol, red, S);
 }
 
 struct CgWork {
@@ -262,7 +291,8 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
 {
     ob200_context *ctx = A->ctx;
     const int32_t n = A->neq;
-    const int P = ctx->shape.sms * 4;                   // blocks of every reducing kernel
+    const int P = kCgMaxBlocks;                         // stride between the partial arrays
+    const int G = ctx->shape.grid(n, kCgThreads, 8);    // CTAs of the vector kernels (<= 148*8 <= P)
     const int64_t need = 3 * (int64_t) n + (int64_t) kRedMax * P + kRedMax + 16;
     if ( A->work.n < need ) OB_CHECK( A->work.alloc(need) );
     CgWork w;
@@ -274,6 +304,7 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
     w.S = reinterpret_cast< CgScalars * >( w.red + kRedMax + 1 );
     OB_CUDA( cudaMemsetAsync(w.partials, 0, sizeof( double ) * ( (size_t) kRedMax * P + kRedMax + 16 ), ctx->stream) );
     const unsigned char *owned = comm ? comm->owned.p : nullptr;
+    const bool dist = comm && comm->nranks > 1;
 
     // preconditioner (IMLSolver::solve re-inits when the matrix version changed, imlsolver.C:110-114)
     const double *diag = nullptr;
@@ -304,18 +335,20 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
         OB_REQUIRE(precond == OB200_PRECOND_VOID, OB200_EINVAL, "cg_solve: unknown preconditioner type %d", precond);
     }
 
-    auto reduce = [&](int nred) -> int {
-        OB_LAUNCH(ctx, cg_reduce_kernel, 1, kCgThreads, 0, w.partials, P, nred, w.red, w.S);
-        if ( comm ) OB_CHECK( comm_allreduce_sum(comm, w.red, nred) );
+    // distributed: all-reduce the locally reduced sums, then the scalar update in its own launch
+    auto finish = [&](int stage, int iter, int nred) -> int {
+        if ( !dist ) return OB200_OK;
+        OB_CHECK( comm_allreduce_sum(comm, w.red, nred) );
+        OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, stage, iter, tol, w.red, w.S);
         return OB200_OK;
     };
 
     // r = b - A x, resid test (cg.h:31-43)
     OB_CHECK( spmv(A, x_dev, w.q) );
     if ( comm ) OB_CHECK( comm_exchange_add(comm, w.q) );
-    OB_LAUNCH(ctx, cg_init_kernel, P, kCgThreads, 0, n, b_dev, w.q, w.r, diag, owned, w.partials, P);
-    OB_CHECK( reduce(3) );
-    OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 0, 0, tol, w.red, w.S);
+    if ( dist ) OB_LAUNCH(ctx, cg_init_kernel< false >, G, kCgThreads, 0, n, b_dev, w.q, w.r, diag, owned, w.partials, P, w.red, tol, w.S);
+    else OB_LAUNCH(ctx, cg_init_kernel< true >, G, kCgThreads, 0, n, b_dev, w.q, w.r, diag, owned, w.partials, P, w.red, tol, w.S);
+    OB_CHECK( finish(0, 0, 3) );
 
     CgScalars h;
     const int poll = 8;
@@ -325,19 +358,21 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
         int batch_end = it + poll < max_iter ? it + poll : max_iter;
         for ( ; it < batch_end; ) {
             it++;
-            OB_LAUNCH(ctx, cg_update_p_kernel, P, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
+            OB_LAUNCH(ctx, cg_update_p_kernel, G, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
             if ( !comm ) {
-                OB_LAUNCH(ctx, cg_spmv_kernel< true >, P, kCgThreads, 0, n, A->rowptr.p, A->colind.p, A->val.p, w.p, w.q, w.partials, w.S);
+                int nb = 0;
+                OB_CHECK( spmv_fused_dot(A, w.p, w.q, w.partials, &nb, &w.S->done) );      // q = A p, partials of p.q
+                OB_LAUNCH(ctx, cg_pq_kernel< true >, 1, kCgThreads, 0, w.partials, nb, w.red, w.S);
             } else {
-                OB_LAUNCH(ctx, cg_spmv_kernel< false >, P, kCgThreads, 0, n, A->rowptr.p, A->colind.p, A->val.p, w.p, w.q, w.partials, w.S);
+                OB_CHECK( spmv_fused_dot(A, w.p, w.q, nullptr, nullptr, &w.S->done) );
                 OB_CHECK( comm_exchange_add(comm, w.q) );
-                OB_LAUNCH(ctx, cg_dot_kernel, P, kCgThreads, 0, n, w.p, w.q, owned, w.partials, w.S);
+                OB_LAUNCH(ctx, cg_dot_kernel, G, kCgThreads, 0, n, w.p, w.q, owned, w.partials, w.red, w.S);
+                if ( dist ) OB_CHECK( finish(1, it, 1) );
+                else OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 1, it, tol, w.red, w.S);
             }
-            OB_CHECK( reduce(1) );
-            OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 1, it, tol, w.red, w.S);
-            OB_LAUNCH(ctx, cg_update_xr_kernel, P, kCgThreads, 0, n, x_dev, w.r, w.p, w.q, diag, owned, w.partials, P, w.S);
-            OB_CHECK( reduce(2) );
-            OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 2, it, tol, w.red, w.S);
+            if ( dist ) OB_LAUNCH(ctx, cg_update_xr_kernel< false >, G, kCgThreads, 0, n, x_dev, w.r, w.p, w.q, diag, owned, w.partials, P, w.red, it, tol, w.S);
+            else OB_LAUNCH(ctx, cg_update_xr_kernel< true >, G, kCgThreads, 0, n, x_dev, w.r, w.p, w.q, diag, owned, w.partials, P, w.red, it, tol, w.S);
+            OB_CHECK( finish(2, it, 2) );
         }
         OB_CUDA( cudaMemcpyAsync(&h, w.S, sizeof( CgScalars ), cudaMemcpyDeviceToHost, ctx->stream) );
         OB_CUDA( cudaStreamSynchronize(ctx->stream) );

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "elemset.h"
 #include "scan.cuh"
+#include "spmv.cuh"
 #include <limits.h>
 
 namespace ob200 {
@@ -139,21 +140,40 @@ __global__ void scale_kernel(double *__restrict__ v, int64_t n, double s)
     for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) v[t] *= s;
 }
 
-// y = A x, one warp per row, coalesced loads of val / colind along the row, shuffle reduction.
+// y = A x, one warp per row straight from global memory (fallback for very long rows)
+template< bool FUSE_DOT >
 __global__ void __launch_bounds__(256)
-spmv_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-            const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+spmv_rowwarp_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                    const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                    double *__restrict__ partials, const int *__restrict__ done)
 {
+    __shared__ double scratch[8];
+    if ( done && *done ) return;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
     const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    double pq = 0.0;
     for ( int64_t row = warp0; row < neq; row += nwarps ) {
         const int b = rowptr[row], e = rowptr[row + 1];
         double s = 0.0;
         for ( int t = b + lane; t < e; t += 32 ) s += val[t] * x[colind[t]];
 #pragma unroll
         for ( int o = 16; o > 0; o >>= 1 ) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ( lane == 0 ) y[row] = s;
+        if ( lane == 0 ) {
+            y[row] = s;
+            if ( FUSE_DOT ) pq += s * x[row];
+        }
+    }
+    if ( FUSE_DOT ) {
+#pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) pq += __shfl_xor_sync(0xffffffffu, pq, o);
+        if ( lane == 0 ) scratch[threadIdx.x >> 5] = pq;
+        __syncthreads();
+        if ( threadIdx.x == 0 ) {
+            double t = 0.0;
+            for ( int w = 0; w < 8; w++ ) t += scratch[w];
+            partials[blockIdx.x] = t;
+        }
     }
 }
 
@@ -164,12 +184,53 @@ using namespace ob200;
 void ob200_csr_touch(ob200_csr *A) { A->version++; }
 
 namespace ob200 {
-int spmv(ob200_csr *A, const double *x, double *y)
+
+static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done)
 {
+    ob200_context *ctx = A->ctx;
+    if ( nblocks ) *nblocks = 0;
     if ( A->neq == 0 ) return OB200_OK;
-    int grid = A->ctx->shape.grid((int64_t) A->neq * 32, 256, 8);
-    OB_LAUNCH(A->ctx, spmv_kernel, grid, 256, 0, A->neq, A->rowptr.p, A->colind.p, A->val.p, x, y);
+    if ( A->nnz == 0 ) {
+        OB_CUDA( cudaMemsetAsync(y, 0, sizeof( double ) * (size_t) A->neq, ctx->stream) );
+        return OB200_OK;
+    }
+    if ( A->maxrow <= kSpmvSlack && A->chunks.p ) {
+        static bool attr_set = false;
+        const int smem = (int) sizeof( SpmvShared );
+        if ( !attr_set ) {
+            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< false >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
+            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
+            attr_set = true;
+        }
+        int grid = ctx->shape.sms * 2;                 // persistent: 2 CTAs per SM, 3 stages each in flight
+        if ( grid > A->nchunks ) grid = A->nchunks;
+        if ( partials ) {
+            OB_LAUNCH(ctx, spmv_stream_kernel< true >, grid, kSpmvThreads, smem, A->neq, A->rowptr.p, A->colind.p, A->val.p,
+                      A->chunks.p, A->nchunks, x, y, partials, done);
+            if ( nblocks ) *nblocks = grid;
+        } else {
+            OB_LAUNCH(ctx, spmv_stream_kernel< false >, grid, kSpmvThreads, smem, A->neq, A->rowptr.p, A->colind.p, A->val.p,
+                      A->chunks.p, A->nchunks, x, y, partials, done);
+        }
+        return OB200_OK;
+    }
+    // rows longer than the streamed kernel's stage: warp per row straight from global memory
+    int grid = ctx->shape.grid((int64_t) A->neq * 32, 256, 8);
+    if ( partials ) {
+        OB_LAUNCH(ctx, spmv_rowwarp_kernel< true >, grid, 256, 0, A->neq, A->rowptr.p, A->colind.p, A->val.p, x, y, partials, done);
+        if ( nblocks ) *nblocks = grid;
+    } else {
+        OB_LAUNCH(ctx, spmv_rowwarp_kernel< false >, grid, 256, 0, A->neq, A->rowptr.p, A->colind.p, A->val.p, x, y, partials, done);
+    }
     return OB200_OK;
+}
+
+int spmv(ob200_csr *A, const double *x, double *y) { return spmv_launch(A, x, y, nullptr, nullptr, nullptr); }
+
+// q = A p with per-CTA partial sums of p.q in partials[0 .. *nblocks) (partials may be null: plain product)
+int spmv_fused_dot(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done)
+{
+    return spmv_launch(A, x, y, partials, nblocks, done);
 }
 } // namespace ob200
 
@@ -250,14 +311,19 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
     OB_CHECK( exclusive_scan(ctx, rowcount.p, rp64.p, (int64_t) neq + 1, &nnz) );
     // CompCol stores colptr / rowind in IntArray (32-bit): keep the same limit and say so
     OB_REQUIRE(nnz < (int64_t) INT_MAX, OB200_ECAPACITY, "csr_build_structure: nnz=%lld exceeds the 32-bit range of the reference's IntArray", (long long) nnz);
-    OB_CHECK( A->rowptr.alloc(neq + 1) );
+    OB_CHECK( A->rowptr.alloc(neq + 1 + kCsrPad) );
     OB_CHECK( narrow_i64_to_i32(ctx, rp64.p, A->rowptr.p, (int64_t) neq + 1) );
-    OB_CHECK( A->colind.alloc(nnz > 0 ? nnz : 1) );
-    OB_CHECK( A->val.alloc(nnz > 0 ? nnz : 1) );
+    OB_CHECK( A->colind.alloc(nnz + kCsrPad) );
+    OB_CHECK( A->val.alloc(nnz + kCsrPad) );
+    OB_CUDA( cudaMemsetAsync(A->colind.p + nnz, 0, sizeof( int32_t ) * kCsrPad, ctx->stream) );
+    OB_CHECK( max_reduce(ctx, rowcount.p, neq, &A->maxrow) );
+    A->nchunks = nnz > 0 ? (int32_t)( ( nnz - 1 ) / kSpmvChunk + 1 ) : 0;
+    OB_CHECK( A->chunks.alloc(A->nchunks + 1) );
+    OB_LAUNCH(ctx, spmv_chunk_table_kernel, ctx->shape.grid((int64_t) neq + 1, 256, 8), 256, 0, neq, A->rowptr.p, A->nchunks, A->chunks.p);
     if ( neq )
         OB_LAUNCH(ctx, row_pattern_kernel< true >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
                   (int32_t *) nullptr, A->rowptr.p, A->colind.p, flag.p + 1);
-    OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t)( nnz > 0 ? nnz : 1 ), ctx->stream) );
+    OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t)( nnz + kCsrPad ), ctx->stream) );
     OB_CUDA( cudaMemcpyAsync(hflag, flag.p, sizeof( int ) * 2, cudaMemcpyDeviceToHost, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
     OB_REQUIRE(hflag[1] == 0, OB200_ECAPACITY, "csr_build_structure: internal row buffer overflow");

@@ -575,3 +575,40 @@ int ob200_elemset_set_state(ob200_elemset *S, const double *state, int on_device
 }
 
 } // extern "C"
+
+// ---- scratch probes (not part of the ABI; used by scripts/probe_atomics.py) ----------------
+namespace ob200 {
+// mode 0: RED.F64 through the slot map, no math; mode 1: plain store through the slot map;
+// mode 2: slot-map read only
+__global__ void __launch_bounds__(256) probe_scatter_kernel(const int32_t *__restrict__ slot, double *__restrict__ val,
+                                                             int64_t nelem, int mode, int *sink)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    int acc = 0;
+    for ( int64_t e = warp0; e < nelem; e += nwarps ) {
+        const int32_t *sl = slot + e * 576;
+#pragma unroll 6
+        for ( int t = lane; t < 576; t += 32 ) {
+            int32_t p = sl[t];
+            if ( mode == 2 ) acc += p;
+            else if ( p >= 0 ) {
+                if ( mode == 0 ) atomicAdd(val + p, 1.0);
+                else val[p] = 1.0;
+            }
+        }
+    }
+    if ( mode == 2 && acc == 123456789 ) *sink = acc;
+}
+}
+extern "C" int ob200_debug_probe_scatter(ob200_elemset *S, ob200_csr *A, int mode, int blocks_per_sm)
+{
+    if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
+    const int32_t *rowptr, *colind;
+    double *val;
+    OB_CHECK( ob200_csr_device_arrays(A, &rowptr, &colind, &val) );
+    int grid = S->ctx->shape.sms * blocks_per_sm;
+    OB_LAUNCH(S->ctx, probe_scatter_kernel, grid, 256, 0, S->slot.p, val, S->nelem, mode, (int *) S->slot.p);
+    return OB200_OK;
+}

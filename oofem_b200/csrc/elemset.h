@@ -17,13 +17,19 @@ struct ElemSetView {
 };
 } // namespace ob200
 
+constexpr int kCsrPad = 8;
+
 struct ob200_csr {
     ob200_context *ctx = nullptr;
     int32_t neq = 0;
     int64_t nnz = 0;
     int64_t version = 0;
-    ob200::DevBuf< int32_t > rowptr, colind;
+    ob200::DevBuf< int32_t > rowptr, colind;     // colind / val padded by kCsrPad entries (16-byte TMA granules)
     ob200::DevBuf< double > val;
+    // streamed SpMV (spmv.cuh): per-chunk {first row, first entry}
+    ob200::DevBuf< int2 > chunks;
+    int32_t nchunks = 0;
+    int32_t maxrow = 0;                           // longest row
     // CG work vectors (allocated on first solve)
     ob200::DevBuf< double > work;
     ob200::DevBuf< double > diag;

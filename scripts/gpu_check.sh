@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, smoke, bench, ncu launch list, ncu full capture of the top kernels.
+# Usage (under gpurun): bash scripts/gpu_check.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+echo "== pytest -m gpu" 
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke_$TAG.log
+echo "== bench"
+timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+echo "== bench reference arm"
+timeout 900 python bench.py --impl reference --steps 2 --warmup 0 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 1 --cg-iters 20 --no-cpu-baseline --no-e2e > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
+echo "== ncu full"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'cg_spmv_kernel|lspace_stiffness_kernel|cg_update_xr_kernel' -s 6 -c 6 \
+    -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --cg-iters 4 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+ls -la $OUT

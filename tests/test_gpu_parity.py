@@ -174,7 +174,14 @@ def test_mises_material_point_vs_oracle(ctx, etype):
         assert np.abs(Ke - Ke.transpose(0, 2, 1)).max() > 0.0
         dom.elems.updateYourself()
         orc.mises_commit(md.state)
-    # unsymmetric element matrices land transposed-correctly in the row storage
+    # unsymmetric element matrices land transposed-correctly in the row storage (one more
+    # plastic increment, NOT committed: after the commit dKappa = 0 and the tangent is elastic)
+    u = rng.normal(size=pb.coords.shape) * 8e-3
+    dom.elems.giveInternalForcesVector(u)
+    orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams,
+                              u[pb.conn - 1].reshape(pb.conn.shape[0], -1), md.state)
+    Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, md.state)
+    assert np.abs(Ke_o - Ke_o.transpose(0, 2, 1)).max() > 0.0
     A = CudaCSR(ctx)
     A.buildInternalStructure(dom.loc, dom.neq)
     dom.elems.assembleStiffness(A)
