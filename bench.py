@@ -382,8 +382,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------
     peak, peak_src = load_peaks()
-    spmv_name = "cg_spmv_kernel< true >" if world == 1 else "cg_spmv_kernel< false >"
-    asm_name = "lspace_stiffness_kernel< OUT_CSR >"
+    spmv_name = "spmv_stream_kernel< true >" if world == 1 else "spmv_stream_kernel< false >"
+    asm_name = next((k for k in ("lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
+                                 "lspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_gather_kernel< false >")
     ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
     ms_asmk, n_asmk = prof.get(asm_name, (0.0, 0))
     # algorithmic bytes: SpMV reads val (8 B) + colind (4 B) per non-zero, and per
@@ -391,9 +392,9 @@ def run_ours(args):
     spmv_bytes = 12.0 * nnz + 20.0 * neq
     spmv_dur = ms_spmv / max(n_spmv, 1) * 1e-3
     spmv_gbs = spmv_bytes / spmv_dur / 1e9 if spmv_dur > 0 else 0.0
-    # assembly: conn (32 B) + matid (4 B) + slot map (576 x 4 B) per element, coordinates once per node
+    # assembly: per element conn (32 B) + matid (4 B) + location array (96 B), coordinates once per node
     # (24 B), every matrix value written once (8 B per non-zero)
-    asm_bytes = nelem * (32.0 + 4.0 + 2304.0) + pb["coords"].shape[0] * 24.0 + 8.0 * nnz
+    asm_bytes = nelem * (32.0 + 4.0 + 96.0) + pb["coords"].shape[0] * 24.0 + 8.0 * nnz
     asm_dur = ms_asmk / max(n_asmk, 1) * 1e-3
     asm_gbs = asm_bytes / asm_dur / 1e9 if asm_dur > 0 else 0.0
     kernel_share = {k: round(v[0] / (t_step * args.steps) , 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
@@ -424,7 +425,7 @@ def run_ours(args):
         "roofline_assembly": {"kernel": asm_name, "bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s",
                               "frac": asm_gbs / peak, "traffic": None, "algorithmic_bytes_per_launch": asm_bytes,
                               "avg_launch_ms": asm_dur * 1e3, "launches": n_asmk,
-                              "note": "FP64-pipe bound rather than HBM bound, see DESIGN.md"},
+                              "note": "owner-computes gather; FP64-pipe bound, see DESIGN.md"},
         "kernel_time_share": kernel_share,
         "e2e": {"value": total_elems / e_asm, "unit": "elements/s", "pcg_iters_per_s": args.cg_iters / e_cg,
                 "h2d_bytes_per_step": int(h2d_asm + h2d_cg), "d2h_bytes_per_step": int(d2h_cg),

@@ -183,6 +183,15 @@ using namespace ob200;
 
 void ob200_csr_touch(ob200_csr *A) { A->version++; }
 
+int ob200_csr_materialize(ob200_csr *A)
+{
+    if ( A->zero_pending ) {
+        if ( A->nnz ) OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t) A->nnz, A->ctx->stream) );
+        A->zero_pending = false;
+    }
+    return OB200_OK;
+}
+
 namespace ob200 {
 
 static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done)
@@ -190,6 +199,7 @@ static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partial
     ob200_context *ctx = A->ctx;
     if ( nblocks ) *nblocks = 0;
     if ( A->neq == 0 ) return OB200_OK;
+    OB_CHECK( ob200_csr_materialize(A) );
     if ( A->nnz == 0 ) {
         OB_CUDA( cudaMemsetAsync(y, 0, sizeof( double ) * (size_t) A->neq, ctx->stream) );
         return OB200_OK;
@@ -331,6 +341,7 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
     A->nnz = nnz;
     A->version++;
     A->diag_version = -1;
+    A->zero_pending = false;
     return OB200_OK;
 }
 
@@ -348,6 +359,7 @@ int ob200_csr_get_structure(const ob200_csr *A, int32_t *rowptr, int32_t *colind
 int ob200_csr_get_values(const ob200_csr *A, double *val, int on_device)
 {
     OB_REQUIRE(A && val, OB200_EINVAL, "csr_get_values: null argument");
+    OB_CHECK( ob200_csr_materialize(const_cast< ob200_csr * >( A )) );
     if ( A->nnz )
         OB_CUDA( cudaMemcpyAsync(val, A->val.p, sizeof( double ) * (size_t) A->nnz,
                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, A->ctx->stream) );
@@ -358,6 +370,7 @@ int ob200_csr_get_values(const ob200_csr *A, double *val, int on_device)
 int ob200_csr_set_values(ob200_csr *A, const double *val, int on_device)
 {
     OB_REQUIRE(A && val, OB200_EINVAL, "csr_set_values: null argument");
+    A->zero_pending = false;
     if ( A->nnz )
         OB_CUDA( cudaMemcpyAsync(A->val.p, val, sizeof( double ) * (size_t) A->nnz,
                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, A->ctx->stream) );
@@ -369,6 +382,7 @@ int ob200_csr_set_values(ob200_csr *A, const double *val, int on_device)
 int ob200_csr_device_arrays(ob200_csr *A, const int32_t **rowptr, const int32_t **colind, double **val)
 {
     OB_REQUIRE(A, OB200_EINVAL, "csr_device_arrays: null matrix");
+    OB_CHECK( ob200_csr_materialize(A) );
     if ( rowptr ) *rowptr = A->rowptr.p;
     if ( colind ) *colind = A->colind.p;
     if ( val ) *val = A->val.p;
@@ -378,7 +392,7 @@ int ob200_csr_device_arrays(ob200_csr *A, const int32_t **rowptr, const int32_t 
 int ob200_csr_zero(ob200_csr *A)
 {
     OB_REQUIRE(A, OB200_EINVAL, "csr_zero: null matrix");
-    if ( A->nnz ) OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t) A->nnz, A->ctx->stream) );
+    A->zero_pending = true;         // performed by the next reader / partial writer, absorbed by a full overwrite
     A->version++;
     return OB200_OK;
 }
@@ -386,6 +400,7 @@ int ob200_csr_zero(ob200_csr *A)
 int ob200_csr_scale(ob200_csr *A, double s)
 {
     OB_REQUIRE(A, OB200_EINVAL, "csr_scale: null matrix");
+    OB_CHECK( ob200_csr_materialize(A) );
     if ( A->nnz ) {
         int grid = A->ctx->shape.grid(A->nnz, 256, 8);
         OB_LAUNCH(A->ctx, scale_kernel, grid, 256, 0, A->val.p, A->nnz, s);
@@ -400,6 +415,7 @@ int ob200_csr_assemble(ob200_csr *A, int64_t nelem, int32_t nd, const int32_t *l
     OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "csr_assemble: matrix has no structure");
     OB_REQUIRE(nd > 0 && nelem >= 0, OB200_EINVAL, "csr_assemble: dimension of 'k' and 'loc' mismatch");
     if ( nelem == 0 ) return OB200_OK;
+    OB_CHECK( ob200_csr_materialize(A) );
     ob200_context *ctx = A->ctx;
     Staged< int32_t > L;
     Staged< double > M;
@@ -434,6 +450,7 @@ int ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value)
     OB_REQUIRE(A && value, OB200_EINVAL, "csr_at: null argument");
     // CompCol::at (compcol.C:376-390): "Array accessing exception -- out of bounds"
     OB_REQUIRE(i >= 1 && j >= 1 && i <= A->neq && j <= A->neq, OB200_EINVAL, "csr_at: (%d,%d) out of bounds", i, j);
+    OB_CHECK( ob200_csr_materialize(A) );
     int32_t rp[2];
     OB_CUDA( cudaMemcpyAsync(rp, A->rowptr.p + ( i - 1 ), sizeof( int32_t ) * 2, cudaMemcpyDeviceToHost, A->ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );

@@ -433,8 +433,12 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
             delete S;
             return OB200_EINVAL;
         }
-        if ( t == OB200_MAT_MISES ) S->has_state = true;
+        if ( t == OB200_MAT_MISES ) {
+            S->has_state = true;
+            S->all_isole = false;
+        }
     }
+    if ( ( rc = gather_prepare_mesh(S) ) < 0 ) { delete S; return rc; }
     if ( S->has_state ) {
         int64_t n = nelem * S->ngp * OB200_MISES_STATE_DOUBLES;
         if ( ( rc = S->state.alloc(n) ) < 0 ) { delete S; return rc; }
@@ -476,13 +480,10 @@ int ob200_elemset_internal_forces(ob200_elemset *S, const double *u, double *fe,
     return os.finish(S->ctx);
 }
 
-int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
+// element -> CSR slot map of the generic (atomic scatter) path; built on first use
+static int build_slot_map(ob200_elemset *S, ob200_csr *A)
 {
-    OB_REQUIRE(S && A, OB200_EINVAL, "elemset_bind: null argument");
-    const int32_t *rowptr, *colind;
-    double *val;
-    OB_CHECK( ob200_csr_device_arrays(A, &rowptr, &colind, &val) );
-    OB_REQUIRE(rowptr, OB200_EINVAL, "elemset_bind: matrix has no structure (call ob200_csr_build_structure first)");
+    if ( S->slot_built ) return OB200_OK;
     int64_t total = S->nelem * S->nd * S->nd;
     OB_CHECK( S->slot.alloc(total) );
     DevBuf< int > missing;
@@ -490,13 +491,27 @@ int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
     OB_CUDA( cudaMemsetAsync(missing.p, 0, sizeof( int ), S->ctx->stream) );
     if ( total ) {
         int grid = S->ctx->shape.grid(total, 256, 8);
-        OB_LAUNCH(S->ctx, slot_map_kernel, grid, 256, 0, S->loc.p, S->nd, S->nelem, rowptr, colind, S->slot.p, missing.p);
+        OB_LAUNCH(S->ctx, slot_map_kernel, grid, 256, 0, S->loc.p, S->nd, S->nelem, A->rowptr.p, A->colind.p, S->slot.p, missing.p);
     }
     int h = 0;
     OB_CUDA( cudaMemcpyAsync(&h, missing.p, sizeof( int ), cudaMemcpyDeviceToHost, S->ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
     // CompCol::assemble DEBUG branch: "Couldn't find row %d in the sparse structure" (compcol.C:288-290)
     OB_REQUIRE(h == 0, OB200_ESTRUCT, "elemset_bind: %d element entries are not in the sparse structure", h);
+    S->slot_built = true;
+    return OB200_OK;
+}
+
+int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
+{
+    OB_REQUIRE(S && A, OB200_EINVAL, "elemset_bind: null argument");
+    OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "elemset_bind: matrix has no structure (call ob200_csr_build_structure first)");
+    S->bound = nullptr;
+    S->slot_built = false;
+    // preferred: owner-computes gather (no atomics); its preparation also verifies that the
+    // matrix pattern is the one of this element set
+    OB_CHECK( gather_bind(S, A) );
+    if ( !S->gather_ok ) OB_CHECK( build_slot_map(S, A) );
     S->bound = A;
     S->bound_version = ob200_csr_rows(A);
     return OB200_OK;
@@ -506,10 +521,14 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
 {
     OB_REQUIRE(S && A, OB200_EINVAL, "elemset_assemble_stiffness: null argument");
     if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
-    const int32_t *rowptr, *colind;
-    double *val;
-    OB_CHECK( ob200_csr_device_arrays(A, &rowptr, &colind, &val) );
-    OB_CHECK( launch_stiffness(S, OUT_CSR, val, S->slot.p, nullptr) );
+    if ( S->gather_ok ) {
+        if ( S->nelem ) OB_CHECK( gather_assemble_lspace(S, A) );
+        ob200_csr_touch(A);
+        return OB200_OK;
+    }
+    OB_CHECK( build_slot_map(S, A) );
+    OB_CHECK( ob200_csr_materialize(A) );
+    OB_CHECK( launch_stiffness(S, OUT_CSR, A->val.p, S->slot.p, nullptr) );
     ob200_csr_touch(A);
     return OB200_OK;
 }
@@ -605,6 +624,7 @@ __global__ void __launch_bounds__(256) probe_scatter_kernel(const int32_t *__res
 extern "C" int ob200_debug_probe_scatter(ob200_elemset *S, ob200_csr *A, int mode, int blocks_per_sm)
 {
     if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
+    OB_CHECK( build_slot_map(S, A) );
     const int32_t *rowptr, *colind;
     double *val;
     OB_CHECK( ob200_csr_device_arrays(A, &rowptr, &colind, &val) );

@@ -30,6 +30,9 @@ struct ob200_csr {
     ob200::DevBuf< int2 > chunks;
     int32_t nchunks = 0;
     int32_t maxrow = 0;                           // longest row
+    // SparseMtrx::zero() is lazy: the memset is skipped when the next writer overwrites every entry
+    // (the gather assembly does); any other reader/writer materialises it first (csr_materialize)
+    bool zero_pending = false;
     // CG work vectors (allocated on first solve)
     ob200::DevBuf< double > work;
     ob200::DevBuf< double > diag;
@@ -46,6 +49,18 @@ struct ob200_elemset {
     ob200::DevBuf< int32_t > conn, matid, loc, slot;
     ob200_csr *bound = nullptr;
     int64_t bound_version = -1;
+    bool slot_built = false;
+    // owner-computes ("gather") assembly, assemble_gather.cu: node -> element incidence, built at create
+    int32_t maxval = 0;                            // largest number of elements around a node
+    int64_t nvisit = 0;                            // nelem * nen
+    ob200::DevBuf< int32_t > ninc_start, ninc, ninc_node, nodeeq;
+    // ... and what depends on the bound matrix
+    bool gather_ok = false, covers_all = false;
+    int32_t maxblk = 0, ngroups = 0;
+    ob200::DevBuf< unsigned char > pos, nblk;
+    ob200::DevBuf< unsigned short > blk;
+    ob200::DevBuf< int2 > gtab;
+    bool all_isole = true;
     int64_t neq_hint() const { return neq; }
     ob200::ElemSetView view() const
     {
@@ -56,3 +71,11 @@ struct ob200_elemset {
 
 // bump the matrix version after its values changed (SparseMtrx::version)
 void ob200_csr_touch(ob200_csr *A);
+// perform a pending lazy zero()
+int ob200_csr_materialize(ob200_csr *A);
+
+namespace ob200 {
+int gather_prepare_mesh(ob200_elemset *S);                       // at create: incidence, nodeeq
+int gather_bind(ob200_elemset *S, ob200_csr *A);                 // at bind: block schedule, group table
+int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A);      // the kernel
+}

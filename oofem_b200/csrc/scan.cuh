@@ -49,7 +49,7 @@ __global__ void scan_tile_kernel(const TIn *__restrict__ in, int64_t *__restrict
     if ( threadIdx.x == kScanThreads - 1 ) tile_sums[blockIdx.x] = warp_sums[kScanThreads / 32 - 1];
 }
 
-__global__ void scan_add_kernel(int64_t *__restrict__ out, int64_t n, const int64_t *__restrict__ tile_offsets)
+static __global__ void scan_add_kernel(int64_t *__restrict__ out, int64_t n, const int64_t *__restrict__ tile_offsets)
 {
     const int64_t off = tile_offsets[blockIdx.x];
     const int64_t base = (int64_t) blockIdx.x * kScanTile;
@@ -90,7 +90,7 @@ inline int exclusive_scan(ob200_context *ctx, const int32_t *in, int64_t *out, i
     return OB200_OK;
 }
 
-__global__ void max_reduce_kernel(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out)
+static __global__ void max_reduce_kernel(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out)
 {
     int32_t m = 0;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
@@ -113,7 +113,7 @@ inline int max_reduce(ob200_context *ctx, const int32_t *in, int64_t n, int32_t 
     return OB200_OK;
 }
 
-__global__ void narrow_kernel(const int64_t *__restrict__ in, int32_t *__restrict__ out, int64_t n)
+static __global__ void narrow_kernel(const int64_t *__restrict__ in, int32_t *__restrict__ out, int64_t n)
 {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) out[t] = (int32_t) in[t];
