@@ -30,7 +30,7 @@ constexpr int kGatherVisits = kGroupVisits + kMaxValence;    // most visits a gr
 constexpr int kGatherThreads = 4 * kGroupVisits;     // 128: four lanes per visit; a group's few extra visits take a second pass
 constexpr int kGatherWarps = kGatherThreads / 32;
 constexpr int kMaxRowLen = 128;                      // longest row laid out in shared memory
-constexpr int kBlkDoubles = 9;
+constexpr int kBlkDoubles = 10;                     // a parked 3x3 block, padded to 80 B (16-byte aligned)
 
 // ---- mesh-only preprocessing (elemset create) ---------------------------------------------
 
@@ -57,8 +57,7 @@ __global__ void node_incidence_fill_kernel(const int32_t *__restrict__ conn, int
 
 // sort each node's visits (ascending element number): the accumulation order must not depend on
 // the order in which the atomics above happened to land
-__global__ void node_incidence_sort_kernel(int64_t nnode, const int32_t *__restrict__ start, int32_t *__restrict__ ninc,
-                                           int32_t *__restrict__ ninc_node)
+__global__ void node_incidence_sort_kernel(int64_t nnode, const int32_t *__restrict__ start, int32_t *__restrict__ ninc)
 {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for ( int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < nnode; w += stride ) {
@@ -69,7 +68,18 @@ __global__ void node_incidence_sort_kernel(int64_t nnode, const int32_t *__restr
             while ( j >= b && ninc[j] > v ) { ninc[j + 1] = ninc[j]; j--; }
             ninc[j + 1] = v;
         }
-        for ( int i = b; i < e; i++ ) ninc_node[i] = (int32_t) w;
+    }
+}
+
+// parking base of every visit: 8 * (first visit of its node - first visit of the node's group)
+__global__ void visit_base_kernel(int64_t nnode, const int32_t *__restrict__ start, const int2 *__restrict__ gtab, int32_t *__restrict__ vbase)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; w < nnode; w += stride ) {
+        const int b = start[w], e = start[w + 1];
+        if ( e == b ) continue;
+        const int base = ( b - gtab[b / kGroupVisits].y ) * 8;
+        for ( int i = b; i < e; i++ ) vbase[i] = base;
     }
 }
 
@@ -83,6 +93,18 @@ __global__ void node_equations_kernel(const int32_t *__restrict__ conn, const in
         int node = conn[t] - 1;
 #pragma unroll
         for ( int i = 0; i < 3; i++ ) nodeeq[(int64_t) node * 3 + i] = loc[t * 3 + i];
+    }
+}
+
+// vertex coordinates gathered per element: exyz[e][3*k + i] = coords[conn[e][k]][i]
+__global__ void element_coords_kernel(const int32_t *__restrict__ conn, const double *__restrict__ coords, int64_t n, double *__restrict__ exyz)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) {
+        const double *c = coords + (int64_t)( conn[t] - 1 ) * 3;
+        exyz[t * 3] = c[0];
+        exyz[t * 3 + 1] = c[1];
+        exyz[t * 3 + 2] = c[2];
     }
 }
 
@@ -146,46 +168,61 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
                 if ( !ok ) atomicAdd(flags, 1);
             }
         }
-        // pass 1: items with a smaller key, same key before me, same key in total
-        int less[Q], same_before[Q];
-#pragma unroll
-        for ( int q = 0; q < Q; q++ ) less[q] = same_before[q] = 0;
         const int nq = ( nitems + 31 ) >> 5;
-        for ( int q2 = 0; q2 < nq; q2++ ) {
-            int kq = INT_MAX;
+        // value of per-item register array `arr` of item jt = q2*32 + src, broadcast to the warp
+#define ITEM_BCAST(arr, dflt)                                        \
+    ( [&]() {                                                        \
+        int sel__ = dflt;                                            \
+        _Pragma("unroll") for ( int qs = 0; qs < Q; qs++ ) if ( qs == q2 ) sel__ = arr[qs]; \
+        return __shfl_sync(0xffffffffu, sel__, src);                 \
+    }() )
+        // pass 1: rank inside my key (same key, earlier item) and size of my key
+        int same_before[Q], same_total[Q];
 #pragma unroll
-            for ( int q = 0; q < Q; q++ ) if ( q == q2 ) kq = key[q];
-            for ( int src = 0; src < 32; src++ ) {
+        for ( int q = 0; q < Q; q++ ) same_before[q] = same_total[q] = 0;
+        for ( int q2 = 0; q2 < nq; q2++ )
+            for ( int src = 0; src < 32 && q2 * 32 + src < nitems; src++ ) {
                 const int jt = q2 * 32 + src;
-                if ( jt >= nitems ) break;
-                const int kj = __shfl_sync(0xffffffffu, kq, src);
+                const int kj = ITEM_BCAST(key, INT_MAX);
 #pragma unroll
                 for ( int q = 0; q < Q; q++ ) {
-                    const int it = q * 32 + lane;
-                    less[q] += ( kj < key[q] );
-                    same_before[q] += ( kj == key[q] && jt < it );
+                    same_total[q] += ( kj == key[q] );
+                    same_before[q] += ( kj == key[q] && jt < q * 32 + lane );
                 }
             }
-        }
+        int first[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) first[q] = ( same_before[q] == 0 && cm[q] != 0 ) ? 1 : 0;
         // pass 2: distinct smaller keys (= my column block) and their total width (= my first column)
-        int blkidx[Q], cstart[Q];
+        int blkidx[Q], cstart[Q], width[Q];
 #pragma unroll
-        for ( int q = 0; q < Q; q++ ) blkidx[q] = cstart[q] = 0;
-        for ( int q2 = 0; q2 < nq; q2++ ) {
-            int kq = INT_MAX, fq = 0, wq = 0;
-#pragma unroll
-            for ( int q = 0; q < Q; q++ ) if ( q == q2 ) { kq = key[q]; fq = ( same_before[q] == 0 ); wq = __popc(cm[q]); }
-            for ( int src = 0; src < 32; src++ ) {
-                const int jt = q2 * 32 + src;
-                if ( jt >= nitems ) break;
-                const int kj = __shfl_sync(0xffffffffu, kq, src);
-                const int fj = __shfl_sync(0xffffffffu, fq, src);
-                const int wj = __shfl_sync(0xffffffffu, wq, src);
+        for ( int q = 0; q < Q; q++ ) { blkidx[q] = cstart[q] = 0; width[q] = __popc(cm[q]); }
+        for ( int q2 = 0; q2 < nq; q2++ )
+            for ( int src = 0; src < 32 && q2 * 32 + src < nitems; src++ ) {
+                const int kj = ITEM_BCAST(key, INT_MAX), fj = ITEM_BCAST(first, 0), wj = ITEM_BCAST(width, 0);
 #pragma unroll
                 for ( int q = 0; q < Q; q++ )
                     if ( fj && kj < key[q] ) { blkidx[q]++; cstart[q] += wj; }
             }
-        }
+        // pass 3: parking position.  Blocks are handled 32 at a time (one per lane) by the assembly
+        // kernel, which walks "the i-th item of every block that has one" for i = 0, 1, ...; items are
+        // parked in exactly that order (jagged-diagonal order) so that each step reads contiguous slots.
+        int park[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) park[q] = 0;
+        for ( int q2 = 0; q2 < nq; q2++ )
+            for ( int src = 0; src < 32 && q2 * 32 + src < nitems; src++ ) {
+                const int fj = ITEM_BCAST(first, 0);
+                if ( !fj ) continue;
+                const int bj = ITEM_BCAST(blkidx, 0), cj = ITEM_BCAST(same_total, 0);
+#pragma unroll
+                for ( int q = 0; q < Q; q++ ) {
+                    const int i = same_before[q];
+                    if ( ( bj >> 5 ) < ( blkidx[q] >> 5 ) ) park[q] += cj;
+                    else if ( ( bj >> 5 ) == ( blkidx[q] >> 5 ) ) park[q] += min(cj, i) + ( ( bj < blkidx[q] && cj > i ) ? 1 : 0 );
+                }
+            }
+#undef ITEM_BCAST
         // the node's own rows (any free dof; all of them share the pattern)
         const int r0 = nodeeq[w * 3], r1 = nodeeq[w * 3 + 1], r2 = nodeeq[w * 3 + 2];
         const int row = r0 > 0 ? r0 - 1 : ( r1 > 0 ? r1 - 1 : ( r2 > 0 ? r2 - 1 : -1 ) );
@@ -195,31 +232,26 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
             const int it = q * 32 + lane;
             if ( it < nitems ) {
                 const bool live = cm[q] != 0 && row >= 0;
-                const int p = less[q] + same_before[q];
-                pos[( (int64_t) v0 + ( it >> 3 ) ) * 8 + ( it & 7 )] = (unsigned char)( live ? p : 0xFF );
+                pos[( (int64_t) v0 + ( it >> 3 ) ) * 8 + ( it & 7 )] = (unsigned char)( live ? park[q] : 0xFF );
                 if ( live ) {
-                    if ( p >= 0xFF || blkidx[q] >= maxblk ) atomicAdd(flags + 1, 1);
-                    // the last item of a block (largest position) records where the block ends
+                    if ( park[q] >= 0xFF || blkidx[q] >= maxblk || same_total[q] > 0xFF ) atomicAdd(flags + 1, 1);
                     nb_max = max(nb_max, blkidx[q] + 1);
-                    if ( same_before[q] == 0 ) {
-                        width_total += __popc(cm[q]);
+                    if ( first[q] ) {
+                        width_total += width[q];
                         if ( blkidx[q] < maxblk ) {
-                            // count of this key: filled in below through seg_end (positions are contiguous)
+                            // one entry per column block: number of parked items, free-dof mask of the column node
+                            blk[w * maxblk + blkidx[q]] = (unsigned short)( same_total[q] | ( cm[q] << 8 ) );
                             if ( colind[rowptr[row] + cstart[q]] != key[q] - 1 ) atomicAdd(flags, 1);
                         }
                     }
                 }
             }
         }
-        // seg_end of block n = number of live items with block index <= n: every item bumps its block
-        // (small shared-memory-free approach: lanes publish, block owners count)
-        nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, 16));
-        nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, 8));
-        nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, 4));
-        nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, 2));
-        nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, 1));
 #pragma unroll
-        for ( int o = 16; o > 0; o >>= 1 ) width_total += __shfl_xor_sync(0xffffffffu, width_total, o);
+        for ( int o = 16; o > 0; o >>= 1 ) {
+            nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, o));
+            width_total += __shfl_xor_sync(0xffffffffu, width_total, o);
+        }
         if ( row >= 0 ) {
             if ( width_total != rowptr[row + 1] - rowptr[row] || width_total > kMaxRowLen ) {
                 if ( lane == 0 ) atomicAdd(flags + ( width_total > kMaxRowLen ? 1 : 0 ), 1);
@@ -229,31 +261,6 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
             nblk[w] = (unsigned char)( row >= 0 ? nb_max : 0 );
             // matrix entries this node's rows account for (to know whether the set covers the whole pattern)
             if ( row >= 0 ) atomicAdd(covered, (unsigned long long) width_total * ( ( r0 > 0 ) + ( r1 > 0 ) + ( r2 > 0 ) ));
-        }
-        // seg_end: the item with the largest position inside its block writes position + 1
-        // (it is the one whose same-key count after it is zero); computed with one more sweep
-        if ( row >= 0 ) {
-            int same_total[Q];
-#pragma unroll
-            for ( int q = 0; q < Q; q++ ) same_total[q] = 0;
-            for ( int q2 = 0; q2 < nq; q2++ ) {
-                int kq = INT_MAX;
-#pragma unroll
-                for ( int q = 0; q < Q; q++ ) if ( q == q2 ) kq = key[q];
-                for ( int src = 0; src < 32; src++ ) {
-                    const int jt = q2 * 32 + src;
-                    if ( jt >= nitems ) break;
-                    const int kj = __shfl_sync(0xffffffffu, kq, src);
-#pragma unroll
-                    for ( int q = 0; q < Q; q++ ) same_total[q] += ( kj == key[q] );
-                }
-            }
-#pragma unroll
-            for ( int q = 0; q < Q; q++ ) {
-                const int it = q * 32 + lane;
-                if ( it < nitems && cm[q] != 0 && same_before[q] == 0 && blkidx[q] < maxblk )
-                    blk[w * maxblk + blkidx[q]] = (unsigned short)( ( less[q] + same_total[q] ) | ( cm[q] << 8 ) );
-            }
         }
     }
 }
@@ -268,81 +275,221 @@ struct GatherView {
     int maxblk;
 };
 
+// one pipeline stage: everything phase A needs for one group, written by the producer warp
+struct GatherStage {
+    double xyz[kGatherVisits][26];        // element vertex coordinates per visit (row padded to 208 B: 16-byte rows, bank spread)
+    double lam[kGatherVisits], mu[kGatherVisits];
+    uint2 pos[kGatherVisits];             // parking positions of the 8 blocks
+    int ent[kGatherVisits];               // local node index | parking base << 3
+    int4 meta;                            // first node, first visit, end node, end visit
+};
 struct GatherShared {
-    double park[kGatherVisits * 8 * kBlkDoubles];             // 36,864 B
-    double rows[kGatherWarps][3][kMaxRowLen];                 // 24,576 B
+    GatherStage st[2];                                         // 21,920 B
+    double park[kGatherVisits * 8 * kBlkDoubles];              // 30,720 B
+    double rows[kGatherWarps][3][kMaxRowLen];                  // 12,288 B; phase A reuses it as the quad exchange buffer [12][32]
+    unsigned long long full[2], empty[2];
 };
 
+__device__ __forceinline__ void mbar_init_(unsigned long long *bar, int count)
+{
+    asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"( (uint32_t) __cvta_generic_to_shared(bar) ), "r"( count ) );
+}
+__device__ __forceinline__ void mbar_arrive_(unsigned long long *bar)
+{
+    asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( (uint32_t) __cvta_generic_to_shared(bar) ) : "memory" );
+}
+__device__ __forceinline__ void mbar_wait_(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"( (uint32_t) __cvta_generic_to_shared(bar) ), "r"( parity ) : "memory" );
+}
+
+// 0.125 * (1 +- a)(1 +- a), a = 1/sqrt 3: the values a trilinear shape-function derivative takes at
+// the 2x2x2 Gauss points (FEI3dHexaLin::evaldNdxi, fei3dhexalin.C:129-166; gaussintegrationrule.C:1450)
+__device__ __forceinline__ double hexa_dn_pick(bool a1, bool a2)
+{
+    constexpr double kA = 0.577350269189626;
+    constexpr double cPP = 0.125 * ( 1.0 + kA ) * ( 1.0 + kA ), cPM = 0.125 * ( 1.0 + kA ) * ( 1.0 - kA ),
+                     cMM = 0.125 * ( 1.0 - kA ) * ( 1.0 - kA );
+    return a1 ? ( a2 ? cPP : cPM ) : ( a2 ? cPM : cMM );
+}
+// dN_k/d(xi,eta,zeta) of node k (signs px,py,pz = "+1") at the Gauss point with signs (gu,gv,gw)
+__device__ __forceinline__ void hexa_dn_signs(bool px, bool py, bool pz, bool gu, bool gv, bool gw, double d[3])
+{
+    const bool au = px == gu, av = py == gv, aw = pz == gw;
+    const double t0 = hexa_dn_pick(av, aw), t1 = hexa_dn_pick(au, aw), t2 = hexa_dn_pick(au, av);
+    d[0] = px ? t0 : -t0;
+    d[1] = py ? t1 : -t1;
+    d[2] = pz ? t2 : -t2;
+}
+
+// Persistent, warp-specialised: warp 4 is the producer -- it walks this CTA's groups one ahead of
+// the compute warps and resolves the dependent index chain (group table -> visit -> connectivity ->
+// coordinates, material) into a shared-memory stage; warps 0-3 never wait on that chain.
 template< bool ACCUM >
-__global__ void __launch_bounds__(kGatherThreads, 4)
-lspace_gather_kernel(ElemSetView S, GatherView G, const int32_t *__restrict__ rowptr, double *__restrict__ val)
+__global__ void __launch_bounds__(kGatherThreads + 32, 3)
+lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t *__restrict__ rowptr, double *__restrict__ val)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GatherShared &sh = *reinterpret_cast< GatherShared * >( smem_raw );
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int2 g0 = G.gtab[blockIdx.x], g1 = G.gtab[blockIdx.x + 1];
-    const int nvis = g1.y - g0.y;
-
-    // ---- phase A: four lanes per visit ----
-    // Lane q of the quad inverts the Jacobian at Gauss points 2q, 2q+1 and forms dV * grad N_a there;
-    // the quad then walks the eight Gauss points, the owner broadcasts (J^-1, dV grad N_a) with
-    // shuffles, and every lane accumulates the two blocks K_ab, b = 2q, 2q+1 (18 accumulators).
-    // metadata of the node this warp will reduce first: requested now, consumed after the barrier
-    int b_nb = 0, b_info = 0, b_seg0 = 0, b_eq[3] = { 0, 0, 0 }, b_row[3] = { 0, 0, 0 };
-    if ( g0.x + wid < g1.x ) {
-        const int w = g0.x + wid;
-        b_nb = G.nblk[w];
-        if ( lane < b_nb ) b_info = G.blk[(int64_t) w * G.maxblk + lane];
-        if ( lane > 0 && lane < b_nb ) b_seg0 = G.blk[(int64_t) w * G.maxblk + lane - 1] & 0xFF;
+    if ( tid == 0 ) {
 #pragma unroll
-        for ( int i = 0; i < 3; i++ ) {
-            b_eq[i] = G.nodeeq[(int64_t) w * 3 + i];
-            if ( b_eq[i] > 0 ) b_row[i] = rowptr[b_eq[i] - 1];
+        for ( int s = 0; s < 2; s++ ) {
+            mbar_init_(&sh.full[s], 1);
+            mbar_init_(&sh.empty[s], kGatherWarps);
         }
+        asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
     }
-    for ( int t = tid >> 2; t < ( ( nvis + 7 ) & ~7 ); t += kGroupVisits ) {
-        const int q = tid & 3;
-        const bool live_visit = t < nvis;
-        const int64_t v = (int64_t) g0.y + ( live_visit ? t : 0 );
-        uint2 pw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-        if ( live_visit ) pw = *reinterpret_cast< const uint2 * >( G.pos + v * 8 );
-        // whole quads are live or dead together, whole warps stay converged for the shuffles
-        const bool work = !( pw.x == 0xFFFFFFFFu && pw.y == 0xFFFFFFFFu );
-        if ( __any_sync(0xffffffffu, work) ) {
-            const int ent = work ? G.ninc[v] : 0;
+    __syncthreads();
+    const int nmine = ( ngroups > (int) blockIdx.x ) ? ( ngroups - 1 - (int) blockIdx.x ) / (int) gridDim.x + 1 : 0;
+
+    if ( wid == kGatherWarps ) {
+        // ---- producer ----
+        // Software-pipelined over groups: the visit records of group k+1 (and the table entries of
+        // group k+2) are requested while the connectivity -> coordinate chain of group k resolves.
+        auto stage_visit = [&](GatherStage &st, int t, int ent, int pbase, uint2 pw, bool with_coords) {
             const int64_t e = ent >> 3;
-            const int la = ent & 7;
-            double own[2][12];       // per owned Gauss point: J^-1 (9), dV * grad N_a (3)
+            const MatParams *mp = S.mat + S.matid[e];
+            if ( with_coords ) {
+                const double2 *src = reinterpret_cast< const double2 * >( S.exyz + e * 24 );
+                double2 *dst = reinterpret_cast< double2 * >( st.xyz[t] );
+#pragma unroll
+                for ( int part = 0; part < 12; part++ ) dst[part] = src[part];
+            }
+            double lam, mu;
+            isole_lame(mp->E, mp->nu, lam, mu);
+            st.lam[t] = lam;
+            st.mu[t] = mu;
+            st.pos[t] = pw;
+            st.ent[t] = ( ent & 7 ) | ( pbase << 3 );
+        };
+        int2 g0 = make_int2(0, 0), g1 = g0, h0 = g0, h1 = g0;      // table entries of group k, k+1
+        int ent = 0, pbase = 0;
+        uint2 pw = make_uint2(0, 0);
+        if ( nmine > 0 ) {
+            g0 = G.gtab[blockIdx.x];
+            g1 = G.gtab[blockIdx.x + 1];
+            if ( lane < g1.y - g0.y ) {
+                ent = G.ninc[g0.y + lane];
+                pbase = G.ninc_node[g0.y + lane];
+                pw = *reinterpret_cast< const uint2 * >( G.pos + (int64_t)( g0.y + lane ) * 8 );
+            }
+        }
+        if ( nmine > 1 ) {
+            h0 = G.gtab[blockIdx.x + gridDim.x];
+            h1 = G.gtab[blockIdx.x + gridDim.x + 1];
+        }
+        for ( int k = 0; k < nmine; k++ ) {
+            const int s = k & 1;
+            // requests for the groups behind this one
+            int2 n0 = h0, n1 = h1;
+            int nent = 0, npbase = 0;
+            uint2 npw = make_uint2(0, 0);
+            if ( k + 1 < nmine && lane < h1.y - h0.y ) {
+                nent = G.ninc[h0.y + lane];
+                npbase = G.ninc_node[h0.y + lane];
+                npw = *reinterpret_cast< const uint2 * >( G.pos + (int64_t)( h0.y + lane ) * 8 );
+            }
+            if ( k + 2 < nmine ) {
+                const int g = blockIdx.x + ( k + 2 ) * gridDim.x;
+                n0 = G.gtab[g];
+                n1 = G.gtab[g + 1];
+            }
+            if ( k >= 2 ) mbar_wait_(&sh.empty[s], ( ( k >> 1 ) - 1 ) & 1);
+            GatherStage &st = sh.st[s];
+            const int nvis = g1.y - g0.y;
+            // coordinates of the window's 32 visits: 12 chunks of 16 B per visit, 12 coalesced rounds
             {
-                double xyz[24];
-                const int4 c0 = *reinterpret_cast< const int4 * >( S.conn + e * 8 );
-                const int4 c1 = *reinterpret_cast< const int4 * >( S.conn + e * 8 + 4 );
-                const int nd[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+                double2 buf[12];
 #pragma unroll
-                for ( int k = 0; k < 8; k++ ) {
-                    const double *c = S.coords + (int64_t)( nd[k] - 1 ) * 3;
-                    xyz[3 * k] = c[0]; xyz[3 * k + 1] = c[1]; xyz[3 * k + 2] = c[2];
+                for ( int r = 0; r < 12; r++ ) {           // all twelve loads in flight before the first store
+                    const int c = r * 32 + lane, vis = c / 12, part = c - vis * 12;
+                    const int64_t ev = __shfl_sync(0xffffffffu, ent, vis) >> 3;
+                    buf[r] = reinterpret_cast< const double2 * >( S.exyz + ev * 24 )[part];
                 }
-                double sxa, sya, sza;
-                hexa_signs(la, sxa, sya, sza);
 #pragma unroll
-                for ( int h = 0; h < 2; h++ ) {
-                    double u, vv, ww, Ji[3][3];
-                    hexa_gp(2 * q + h, u, vv, ww);
-                    const double dV = fabs(hexa_jacobian(xyz, u, vv, ww, Ji));
-                    const double fu = 1.0 + sxa * u, fv = 1.0 + sya * vv, fw = 1.0 + sza * ww;
-                    const double da0 = dV * sxa * 0.125 * fv * fw, da1 = dV * sya * 0.125 * fu * fw, da2 = dV * sza * 0.125 * fu * fv;
-#pragma unroll
-                    for ( int i = 0; i < 3; i++ )
-#pragma unroll
-                        for ( int j = 0; j < 3; j++ ) own[h][3 * i + j] = Ji[i][j];
-#pragma unroll
-                    for ( int j = 0; j < 3; j++ ) own[h][9 + j] = da0 * Ji[0][j] + da1 * Ji[1][j] + da2 * Ji[2][j];
+                for ( int r = 0; r < 12; r++ ) {
+                    const int c = r * 32 + lane, vis = c / 12, part = c - vis * 12;
+                    if ( vis < nvis ) reinterpret_cast< double2 * >( st.xyz[vis] )[part] = buf[r];
                 }
             }
-            // the two shape functions of this lane: b = 2q, 2q + 1.  dN_b at a Gauss point is
-            // +-0.125 * {(1+a)^2, (1-a^2), (1-a)^2} (a = 1/sqrt 3), picked by sign agreement between
-            // the node and the Gauss point: selects, no FP64 work
+            if ( lane < nvis ) stage_visit(st, lane, ent, pbase, pw, false);
+            for ( int t = lane + 32; t < nvis; t += 32 ) {           // the few visits beyond the window
+                const int64_t v = (int64_t) g0.y + t;
+                stage_visit(st, t, G.ninc[v], G.ninc_node[v], *reinterpret_cast< const uint2 * >( G.pos + v * 8 ), true);
+            }
+            if ( lane == 0 ) st.meta = make_int4(g0.x, g0.y, g1.x, g1.y);
+            __syncwarp();
+            if ( lane == 0 ) mbar_arrive_(&sh.full[s]);
+            g0 = h0; g1 = h1; h0 = n0; h1 = n1;
+            ent = nent; pbase = npbase; pw = npw;
+        }
+        return;
+    }
+
+    // ---- compute warps ----
+    for ( int k = 0; k < nmine; k++ ) {
+        const int s = k & 1;
+        const GatherStage &st = sh.st[s];
+        mbar_wait_(&sh.full[s], ( k >> 1 ) & 1);
+        const int4 meta = st.meta;
+        const int n0 = meta.x, v0 = meta.y, n1 = meta.z, nvis = meta.w - meta.y;
+
+        // metadata of the node this warp will reduce first: requested now, consumed after the barrier
+        int b_nb = 0, b_info = 0, b_start = 0, b_eq[3] = { 0, 0, 0 }, b_row[3] = { 0, 0, 0 };
+        if ( n0 + wid < n1 ) {
+            const int w = n0 + wid;
+            b_nb = G.nblk[w];
+            b_start = G.ninc_start[w];
+            if ( lane < b_nb ) b_info = G.blk[(int64_t) w * G.maxblk + lane];
+#pragma unroll
+            for ( int i = 0; i < 3; i++ ) b_eq[i] = G.nodeeq[(int64_t) w * 3 + i];
+        }
+
+        // ---- phase A: four lanes per visit ----
+        // Lane q of the quad inverts the Jacobian at Gauss points 2q, 2q+1 and forms dV * grad N_a there;
+        // the quad then walks the eight Gauss points, the owner broadcasts (J^-1, dV grad N_a) with
+        // shuffles, and every lane accumulates the two blocks K_ab, b = 2q, 2q+1 (18 accumulators).
+        for ( int t = tid >> 2; t < ( ( nvis + 7 ) & ~7 ); t += kGroupVisits ) {
+            const int q = tid & 3;
+            const bool live_visit = t < nvis;
+            const int tt = live_visit ? t : 0;
+            const uint2 pw = live_visit ? st.pos[tt] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            // whole quads are live or dead together, whole warps stay converged for the shuffles
+            const bool work = !( pw.x == 0xFFFFFFFFu && pw.y == 0xFFFFFFFFu );
+            if ( !__any_sync(0xffffffffu, work) ) continue;
+            const int entw = st.ent[tt];
+            const int la = entw & 7;
+            // Jacobians of this lane's two Gauss points, 2q (w = -a) and 2q+1 (w = +a), in one sweep over
+            // the vertices (FEI3dHexaLin::evaldNdx, fei3dhexalin.C:186-204)
+            const bool qu = q >= 2, qv = ( q & 1 ) != 0;
+            double J0[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } }, J1[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+            {
+                const double *xv = st.xyz[tt];
+#pragma unroll
+                for ( int kk = 0; kk < 8; kk++ ) {
+                    const bool px = ( kk & 3 ) >= 2, py = ( kk & 3 ) == 1 || ( kk & 3 ) == 2, pz = kk < 4;
+                    double d0[3], d1[3];
+                    hexa_dn_signs(px, py, pz, qu, qv, false, d0);
+                    hexa_dn_signs(px, py, pz, qu, qv, true, d1);
+                    const double x = xv[3 * kk], y = xv[3 * kk + 1], z = xv[3 * kk + 2];
+#pragma unroll
+                    for ( int j = 0; j < 3; j++ ) {
+                        J0[0][j] += x * d0[j]; J0[1][j] += y * d0[j]; J0[2][j] += z * d0[j];
+                        J1[0][j] += x * d1[j]; J1[1][j] += y * d1[j]; J1[2][j] += z * d1[j];
+                    }
+                }
+            }
+            const bool pxa = ( la & 3 ) >= 2, pya = ( la & 3 ) == 1 || ( la & 3 ) == 2, pza = la < 4;
+            // the two shape functions of this lane: b = 2q, 2q + 1
             bool px[2], py[2], pz[2];
 #pragma unroll
             for ( int bb = 0; bb < 2; bb++ ) {
@@ -351,43 +498,60 @@ lspace_gather_kernel(ElemSetView S, GatherView G, const int32_t *__restrict__ ro
                 py[bb] = ( b & 3 ) == 1 || ( b & 3 ) == 2;
                 pz[bb] = b < 4;
             }
-            constexpr double kA = 0.577350269189626;
-            constexpr double cPP = 0.125 * ( 1.0 + kA ) * ( 1.0 + kA ), cPM = 0.125 * ( 1.0 + kA ) * ( 1.0 - kA ),
-                             cMM = 0.125 * ( 1.0 - kA ) * ( 1.0 - kA );
             double acc[2][9];
 #pragma unroll
             for ( int bb = 0; bb < 2; bb++ )
 #pragma unroll
-                for ( int k = 0; k < 9; k++ ) acc[bb][k] = 0.0;
+                for ( int kk = 0; kk < 9; kk++ ) acc[bb][kk] = 0.0;
+            // two rounds (h = 0: the w = -a Gauss points, h = 1: w = +a): every lane inverts its Jacobian of
+            // the round, then the quad walks the four owners
 #pragma unroll
-            for ( int gp = 0; gp < 8; gp++ ) {
-                double m[12];
-#pragma unroll
-                for ( int k = 0; k < 12; k++ ) m[k] = __shfl_sync(0xffffffffu, own[gp & 1][k], gp >> 1, 4);
-                const bool gu = ( gp & 4 ) != 0, gv = ( gp & 2 ) != 0, gw = ( gp & 1 ) != 0;   // hexa_gp: sign of (u, v, w)
-#pragma unroll
-                for ( int bb = 0; bb < 2; bb++ ) {
-                    const bool au = px[bb] == gu, av = py[bb] == gv, aw = pz[bb] == gw;
-                    const double t0 = av ? ( aw ? cPP : cPM ) : ( aw ? cPM : cMM );
-                    const double t1 = au ? ( aw ? cPP : cPM ) : ( aw ? cPM : cMM );
-                    const double t2 = au ? ( av ? cPP : cPM ) : ( av ? cPM : cMM );
-                    const double d0 = px[bb] ? t0 : -t0, d1 = py[bb] ? t1 : -t1, d2 = pz[bb] ? t2 : -t2;
-                    double gb[3];
-#pragma unroll
-                    for ( int j = 0; j < 3; j++ ) gb[j] = d0 * m[j] + d1 * m[3 + j] + d2 * m[6 + j];
+            for ( int h = 0; h < 2; h++ ) {
+                double own[12];          // J^-1 (9), dV * grad N_a (3) at Gauss point 2q + h
+                {
+                    double Ji[3][3], da[3];
+                    const double dV = fabs(inv3(h ? J1 : J0, Ji));      // weight 1 (structural3delement.C:328-338)
+                    hexa_dn_signs(pxa, pya, pza, qu, qv, h == 1, da);
 #pragma unroll
                     for ( int i = 0; i < 3; i++ )
 #pragma unroll
-                        for ( int j = 0; j < 3; j++ ) acc[bb][3 * i + j] += m[9 + i] * gb[j];
+                        for ( int j = 0; j < 3; j++ ) own[3 * i + j] = Ji[i][j];
+#pragma unroll
+                    for ( int j = 0; j < 3; j++ ) own[9 + j] = dV * ( da[0] * Ji[0][j] + da[1] * Ji[1][j] + da[2] * Ji[2][j] );
+                }
+                // publish to the quad through the warp's exchange buffer [12][32]
+                // (16-byte entries [6][4 owners][8 quads]: a read of one owner by the 8 quads is one 128-byte wavefront)
+                double2 *xch = reinterpret_cast< double2 * >( &sh.rows[wid][0][0] );
+                __syncwarp();
+#pragma unroll
+                for ( int kk = 0; kk < 6; kk++ ) xch[kk * 32 + q * 8 + ( lane >> 2 )] = make_double2(own[2 * kk], own[2 * kk + 1]);
+                __syncwarp();
+#pragma unroll 1
+                for ( int src = 0; src < 4; src++ ) {
+                    double m[12];
+#pragma unroll
+                    for ( int kk = 0; kk < 6; kk++ ) {
+                        const double2 mm = xch[kk * 32 + src * 8 + ( lane >> 2 )];
+                        m[2 * kk] = mm.x;
+                        m[2 * kk + 1] = mm.y;
+                    }
+                    const bool gu = src >= 2, gv = ( src & 1 ) != 0, gw = h == 1;     // Gauss point 2 src + h
+#pragma unroll
+                    for ( int bb = 0; bb < 2; bb++ ) {
+                        double d[3], gb[3];
+                        hexa_dn_signs(px[bb], py[bb], pz[bb], gu, gv, gw, d);
+#pragma unroll
+                        for ( int j = 0; j < 3; j++ ) gb[j] = d[0] * m[j] + d[1] * m[3 + j] + d[2] * m[6 + j];
+#pragma unroll
+                        for ( int i = 0; i < 3; i++ )
+#pragma unroll
+                            for ( int j = 0; j < 3; j++ ) acc[bb][3 * i + j] += m[9 + i] * gb[j];
+                    }
                 }
             }
             if ( work ) {
-                double lam, mu;
-                {
-                    const MatParams *mp = S.mat + S.matid[e];
-                    isole_lame(mp->E, mp->nu, lam, mu);
-                }
-                const int base = ( G.ninc_start[G.ninc_node[v]] - g0.y ) * 8;
+                const double lam = st.lam[tt], mu = st.mu[tt];
+                const int base = entw >> 3;
                 const unsigned int pq = q < 2 ? pw.x : pw.y;
 #pragma unroll
                 for ( int bb = 0; bb < 2; bb++ ) {
@@ -395,83 +559,89 @@ lspace_gather_kernel(ElemSetView S, GatherView G, const int32_t *__restrict__ ro
                     if ( p == 0xFFu ) continue;
                     const double *g = acc[bb];
                     const double tr = mu * ( g[0] + g[4] + g[8] );
-                    double *o = sh.park + (size_t)( base + p ) * kBlkDoubles;
-                    o[0] = lam * g[0] + mu * g[0] + tr;
-                    o[1] = lam * g[1] + mu * g[3];
-                    o[2] = lam * g[2] + mu * g[6];
-                    o[3] = lam * g[3] + mu * g[1];
-                    o[4] = lam * g[4] + mu * g[4] + tr;
-                    o[5] = lam * g[5] + mu * g[7];
-                    o[6] = lam * g[6] + mu * g[2];
-                    o[7] = lam * g[7] + mu * g[5];
-                    o[8] = lam * g[8] + mu * g[8] + tr;
+                    double2 *o = reinterpret_cast< double2 * >( sh.park + (size_t)( base + p ) * kBlkDoubles );
+                    o[0] = make_double2(lam * g[0] + mu * g[0] + tr, lam * g[1] + mu * g[3]);
+                    o[1] = make_double2(lam * g[2] + mu * g[6], lam * g[3] + mu * g[1]);
+                    o[2] = make_double2(lam * g[4] + mu * g[4] + tr, lam * g[5] + mu * g[7]);
+                    o[3] = make_double2(lam * g[6] + mu * g[2], lam * g[7] + mu * g[5]);
+                    o[4].x = lam * g[8] + mu * g[8] + tr;
                 }
             }
         }
-    }
-    __syncthreads();
+        // second level of the phase-B metadata (its address arrived during phase A)
+#pragma unroll
+        for ( int i = 0; i < 3; i++ )
+            if ( b_eq[i] > 0 ) b_row[i] = rowptr[b_eq[i] - 1];
+        // the stage has been consumed: hand it back to the producer
+        __syncwarp();
+        if ( lane == 0 ) mbar_arrive_(&sh.empty[s]);
+        asm volatile( "bar.sync 1, %0;" ::"n"( kGatherThreads ) : "memory" );
 
-    // ---- phase B: one warp per node: sum the parked blocks per column block, write the rows ----
-    for ( int w = g0.x + wid; w < g1.x; w += kGatherWarps ) {
-        const bool first = ( w == g0.x + wid );
-        const int nb = first ? b_nb : G.nblk[w];
-        if ( nb == 0 ) continue;
-        int eqs[3], rowbase[3];
+        // ---- phase B: one warp per node: sum the parked blocks per column block, write the rows ----
+        for ( int w = n0 + wid; w < n1; w += kGatherWarps ) {
+            const bool first = ( w == n0 + wid );
+            const int nb = first ? b_nb : G.nblk[w];
+            if ( nb == 0 ) continue;
+            int eqs[3], rowbase[3];
 #pragma unroll
-        for ( int i = 0; i < 3; i++ ) {
-            eqs[i] = first ? b_eq[i] : G.nodeeq[(int64_t) w * 3 + i];
-            rowbase[i] = first ? b_row[i] : ( eqs[i] > 0 ? rowptr[eqs[i] - 1] : 0 );
-        }
-        const int vbase = ( G.ninc_start[w] - g0.y ) * 8;
-        double( *rows )[kMaxRowLen] = sh.rows[wid];
-        int ccarry = 0, rowlen = 0;
-        for ( int n0 = 0; n0 < nb; n0 += 32 ) {
-            const int n = n0 + lane;
-            int info = 0, seg0 = 0;
-            if ( first && n0 == 0 ) {
-                info = b_info;
-                seg0 = b_seg0;
-            } else if ( n < nb ) {
-                info = G.blk[(int64_t) w * G.maxblk + n];
-                seg0 = n > 0 ? ( G.blk[(int64_t) w * G.maxblk + n - 1] & 0xFF ) : 0;
+            for ( int i = 0; i < 3; i++ ) {
+                eqs[i] = first ? b_eq[i] : G.nodeeq[(int64_t) w * 3 + i];
+                rowbase[i] = first ? b_row[i] : ( eqs[i] > 0 ? rowptr[eqs[i] - 1] : 0 );
             }
-            const int seg1 = info & 0xFF, cm = info >> 8;
-            const int width = __popc(cm);
-            int incl = width;                                   // inclusive scan of the widths
+            const int vbase = ( ( first ? b_start : G.ninc_start[w] ) - v0 ) * 8;
+            int ccarry = 0, slot0 = vbase;
+            for ( int nn0 = 0; nn0 < nb; nn0 += 32 ) {
+                const int n = nn0 + lane;
+                int info = 0;
+                if ( first && nn0 == 0 ) info = b_info;
+                else if ( n < nb ) info = G.blk[(int64_t) w * G.maxblk + n];
+                const int cnt = info & 0xFF, cm = info >> 8;
+                const int width = __popc(cm);
+                int incl = width;                                   // inclusive scan of the widths
 #pragma unroll
-            for ( int o = 1; o < 32; o <<= 1 ) {
-                int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if ( lane >= o ) incl += t;
-            }
-            const int cstart = ccarry + incl - width;
-            ccarry += __shfl_sync(0xffffffffu, incl, 31);
-            if ( n < nb ) {
-                double k[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-                for ( int p = seg0; p < seg1; p++ ) {
-                    const double *s = sh.park + (size_t)( vbase + p ) * kBlkDoubles;
-#pragma unroll
-                    for ( int q = 0; q < 9; q++ ) k[q] += s[q];
+                for ( int o = 1; o < 32; o <<= 1 ) {
+                    int tsh = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ( lane >= o ) incl += tsh;
                 }
-                int c = cstart;
-#pragma unroll
-                for ( int j = 0; j < 3; j++ )
-                    if ( cm & ( 1 << j ) ) {
-                        rows[0][c] = k[j];
-                        rows[1][c] = k[3 + j];
-                        rows[2][c] = k[6 + j];
-                        c++;
+                const int cstart = ccarry + incl - width;
+                ccarry += __shfl_sync(0xffffffffu, incl, 31);
+                // step i sums the i-th parked item of every block that has one; the items of a step sit in
+                // consecutive slots (jagged-diagonal order fixed by node_blocks_kernel)
+                double kb[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+                for ( int i = 0;; i++ ) {
+                    const bool active = cnt > i;
+                    const unsigned int mask = __ballot_sync(0xffffffffu, active);
+                    if ( mask == 0 ) break;
+                    if ( active ) {
+                        const int slot = slot0 + __popc(mask & ( ( 1u << lane ) - 1u ));
+                        const double2 *sp = reinterpret_cast< const double2 * >( sh.park + (size_t) slot * kBlkDoubles );
+                        const double2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+                        const double s4 = sp[4].x;
+                        kb[0] += s0.x; kb[1] += s0.y; kb[2] += s1.x; kb[3] += s1.y;
+                        kb[4] += s2.x; kb[5] += s2.y; kb[6] += s3.x; kb[7] += s3.y;
+                        kb[8] += s4;
                     }
-            }
-            rowlen = ccarry;
-        }
-        __syncwarp();
+                    slot0 += __popc(mask);
+                }
+                if ( n < nb ) {
+                    // the lanes of the warp cover the row contiguously (block after block): three 8-byte
+                    // stores per row and lane, merged into full sectors in L2
 #pragma unroll
-        for ( int i = 0; i < 3; i++ ) {
-            if ( eqs[i] <= 0 ) continue;
-            double *dst = val + rowbase[i];
-            for ( int c = lane; c < rowlen; c += 32 ) dst[c] = ACCUM ? dst[c] + rows[i][c] : rows[i][c];
+                    for ( int i = 0; i < 3; i++ ) {
+                        if ( eqs[i] <= 0 ) continue;
+                        double *dst = val + rowbase[i] + cstart;
+                        int c = 0;
+#pragma unroll
+                        for ( int j = 0; j < 3; j++ )
+                            if ( cm & ( 1 << j ) ) {
+                                dst[c] = ACCUM ? dst[c] + kb[3 * i + j] : kb[3 * i + j];
+                                c++;
+                            }
+                    }
+                }
+            }
         }
-        __syncwarp();
+        asm volatile( "bar.sync 1, %0;" ::"n"( kGatherThreads ) : "memory" );     // parking lot free for the next group
     }
 }
 
@@ -507,8 +677,14 @@ int gather_prepare_mesh(ob200_elemset *S)
     OB_CHECK( S->ninc.alloc(n) );
     OB_CHECK( S->ninc_node.alloc(n) );
     OB_LAUNCH(ctx, node_incidence_fill_kernel, grid, 256, 0, S->conn.p, n, S->nen, S->ninc_start.p, fill.p, S->ninc.p);
-    OB_LAUNCH(ctx, node_incidence_sort_kernel, ctx->shape.grid(S->nnode, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p, S->ninc_node.p);
+    OB_LAUNCH(ctx, node_incidence_sort_kernel, ctx->shape.grid(S->nnode, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p);
     OB_CHECK( max_reduce(ctx, cnt.p, S->nnode, &S->maxval) );
+    S->ngroups = (int32_t)( ( S->nvisit - 1 ) / kGroupVisits + 1 );
+    OB_CHECK( S->gtab.alloc(S->ngroups + 1) );
+    OB_LAUNCH(ctx, group_table_kernel, ctx->shape.grid(S->nnode + 1, 256, 8), 256, 0, (int32_t) S->nnode, S->ninc_start.p, S->ngroups, S->gtab.p);
+    OB_LAUNCH(ctx, visit_base_kernel, ctx->shape.grid(S->nnode, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->gtab.p, S->ninc_node.p);
+    OB_CHECK( S->exyz.alloc(n * 3) );
+    OB_LAUNCH(ctx, element_coords_kernel, grid, 256, 0, S->conn.p, S->coords.p, n, S->exyz.p);
     OB_CHECK( S->nodeeq.alloc(S->nnode * 3) );
     OB_CUDA( cudaMemsetAsync(S->nodeeq.p, 0, sizeof( int32_t ) * (size_t) S->nnode * 3, ctx->stream) );
     OB_LAUNCH(ctx, node_equations_kernel, grid, 256, 0, S->conn.p, S->loc.p, S->nelem, S->nen, S->nodeeq.p);
@@ -533,9 +709,6 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     OB_LAUNCH(ctx, node_blocks_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
               S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
               reinterpret_cast< unsigned long long * >( flags.p + 2 ));
-    S->ngroups = (int32_t)( ( S->nvisit - 1 ) / kGroupVisits + 1 );
-    OB_CHECK( S->gtab.alloc(S->ngroups + 1) );
-    OB_LAUNCH(ctx, group_table_kernel, ctx->shape.grid(S->nnode + 1, 256, 8), 256, 0, (int32_t) S->nnode, S->ninc_start.p, S->ngroups, S->gtab.p);
     int h[4] = { 0, 0, 0, 0 };
     OB_CUDA( cudaMemcpyAsync(h, flags.p, sizeof( int ) * 4, cudaMemcpyDeviceToHost, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
@@ -560,13 +733,15 @@ int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A)
     }
     GatherView G{ S->ninc_start.p, S->ninc.p, S->ninc_node.p, S->nodeeq.p, S->pos.p, S->nblk.p, S->blk.p, S->gtab.p, S->maxblk };
     ElemSetView v = S->view();
+    int grid = ctx->shape.sms * 3;                     // persistent: 3 CTAs per SM
+    if ( grid > S->ngroups ) grid = S->ngroups;
     if ( A->zero_pending && !S->covers_all ) OB_CHECK( ob200_csr_materialize(A) );
     if ( A->zero_pending ) {
         // every entry of the pattern is written by exactly one warp: the pending zero() is absorbed
-        OB_LAUNCH(ctx, lspace_gather_kernel< false >, S->ngroups, kGatherThreads, smem, v, G, A->rowptr.p, A->val.p);
+        OB_LAUNCH(ctx, lspace_gather_kernel< false >, grid, kGatherThreads + 32, smem, v, G, S->ngroups, A->rowptr.p, A->val.p);
         A->zero_pending = false;
     } else {
-        OB_LAUNCH(ctx, lspace_gather_kernel< true >, S->ngroups, kGatherThreads, smem, v, G, A->rowptr.p, A->val.p);
+        OB_LAUNCH(ctx, lspace_gather_kernel< true >, grid, kGatherThreads + 32, smem, v, G, S->ngroups, A->rowptr.p, A->val.p);
     }
     return OB200_OK;
 }

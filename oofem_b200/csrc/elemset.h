@@ -14,6 +14,7 @@ struct ElemSetView {
     const MatParams *mat;      // [nmat]
     const int32_t *loc;        // [nelem][nd], 1-based, 0 = prescribed
     MisesState *state;         // [nelem*ngp] or nullptr
+    const double *exyz;        // [nelem][nen*3] vertex coordinates gathered per element (LSpace gather path) or nullptr
 };
 } // namespace ob200
 
@@ -45,7 +46,7 @@ struct ob200_elemset {
     int64_t nnode = 0, nelem = 0;
     int32_t nmat = 0, neq = 0;
     bool has_state = false;
-    ob200::DevBuf< double > coords, mat, state;
+    ob200::DevBuf< double > coords, mat, state, exyz;
     ob200::DevBuf< int32_t > conn, matid, loc, slot;
     ob200_csr *bound = nullptr;
     int64_t bound_version = -1;
@@ -65,7 +66,7 @@ struct ob200_elemset {
     ob200::ElemSetView view() const
     {
         return ob200::ElemSetView{ coords.p, conn.p, matid.p, (const ob200::MatParams *) mat.p, loc.p,
-                                   (ob200::MisesState *) state.p };
+                                   (ob200::MisesState *) state.p, exyz.p };
     }
 };
 
