@@ -49,39 +49,22 @@ def load_peaks():
 # ---------------------------------------------------------------------------------------
 
 def slab_problem(nx, ny, nz, rank, nranks):
-    """Local mesh of rank `rank`: slab [rank*nx, (rank+1)*nx] of a beam nranks*nx long.
-    Returns dict(coords, conn, loc, neq, nodeeq, shared planes)."""
-    from oofem_b200 import meshgen
-    h = 1.0 / ny
-    coords, conn = meshgen.hex_beam(nx, ny, nz, nx * h, 1.0, nz * h)
-    coords[:, 0] += rank * nx * h
-    fixed_mask = np.zeros((coords.shape[0], 3), dtype=bool)
+    """Local mesh of rank `rank`: slab [rank*nx, (rank+1)*nx] of a beam nranks*nx long
+    (oofem_b200.partition.slab_partition), clamped at x = 0, with its own equation numbering."""
+    from oofem_b200 import meshgen, partition
+    part = partition.slab_partition(nx, ny, nz, rank, nranks)
+    fixed_mask = np.zeros((part.coords.shape[0], 3), dtype=bool)
     plane = (ny + 1) * (nz + 1)
     if rank == 0:
         fixed_mask[:plane] = True                       # clamp x = 0
-    nodeeq, neq = meshgen.equation_numbers(coords.shape[0], fixed_mask)
-    loc = meshgen.location_arrays(conn, nodeeq)
-    first = nodeeq[:plane].reshape(-1)                  # shared with rank-1
-    last = nodeeq[-plane:].reshape(-1)                  # shared with rank+1
-    return dict(coords=coords, conn=conn, loc=loc, neq=neq, nodeeq=nodeeq, first=first, last=last, plane=plane)
+    nodeeq, neq = meshgen.equation_numbers(part.coords.shape[0], fixed_mask)
+    loc = meshgen.location_arrays(part.conn, nodeeq)
+    return dict(coords=part.coords, conn=part.conn, loc=loc, neq=neq, nodeeq=nodeeq, part=part, plane=plane)
 
 
 def halo_arrays(pb, rank, nranks):
-    neigh, offs, eqs = [], [0], []
-    owned = np.ones(pb["neq"], dtype=np.uint8)
-    if rank > 0:
-        e = pb["first"][pb["first"] > 0] - 1
-        neigh.append(rank - 1)
-        eqs.append(e)
-        offs.append(offs[-1] + e.size)
-        owned[e] = 0                                    # the lower rank owns the shared plane
-    if rank < nranks - 1:
-        e = pb["last"][pb["last"] > 0] - 1
-        neigh.append(rank + 1)
-        eqs.append(e)
-        offs.append(offs[-1] + e.size)
-    eqs = np.concatenate(eqs).astype(np.int32) if eqs else np.zeros(0, np.int32)
-    return np.array(neigh, np.int32), np.array(offs, np.int64), eqs, owned
+    from oofem_b200 import partition
+    return partition.halo_arrays(pb["part"], pb["nodeeq"], pb["neq"])
 
 
 class ClockSampler:
