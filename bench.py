@@ -254,22 +254,9 @@ def run_ours(args):
     nnz = A.giveNumberOfNonzeros()
     comm = None
     if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = (C.c_char * 128)()
-            check(lib().ob200_comm_unique_id(raw))
-            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
-        idbuf = idbuf.to(dev)
-        dist.broadcast(idbuf, 0)
-        raw = (C.c_char * 128).from_buffer_copy(bytes(idbuf.cpu().numpy().tobytes()))
-
-        class _Comm:
-            pass
-        comm = _Comm()
-        comm.h = C.c_void_p()
-        check(lib().ob200_comm_create(ctx.h, world, rank, raw, C.byref(comm.h)))
-        neigh, offs, eqs, owned = halo_arrays(pb, rank, world)
-        check(lib().ob200_comm_set_halo(comm.h, neq, len(neigh), ptr(neigh), ptr(offs), ptr(eqs), ptr(owned)))
+        from oofem_b200.comm import Comm
+        comm = Comm.from_torch_distributed(ctx, dev)
+        comm.set_halo(neq, *halo_arrays(pb, rank, world))
     solver = CudaCG(ctx, comm).initializeFrom(dict(lstol=0.0, lsiter=args.cg_iters, lsprecond=1))
     b = torch.ones(neq, dtype=torch.float64, device=dev)
     x = torch.zeros(neq, dtype=torch.float64, device=dev)
