@@ -4,11 +4,14 @@
 // (src/core/compcol.C:263-299) for a whole element set without a single atomic: every matrix row
 // is produced by exactly one warp and written once, coalesced -- bit-reproducible run to run.
 //
-//   * A "visit" is one (node, adjacent element) incidence.  One thread per visit integrates the
-//     eight 3x3 blocks K_ab (a = the visited node, b = 0..7) of that element:
-//         G_ab = sum_gp dV (grad N_a)(grad N_b)^T,   K_ab = lambda G + mu G^T + mu tr(G) I
+//   * A "visit" is one (node, adjacent element) incidence.  A CTA first evaluates the geometry of
+//     every DISTINCT element its visits touch, one thread per (element, Gauss point):
+//         g_b = sqrt(dV) grad N_b,  b = 0..7   (FEI3dHexaLin::evaldNdx, fei3dhexalin.C:186-204)
+//     into shared memory, then four threads per visit contract the eight 3x3 blocks K_ab (a = the
+//     visited node, b = 0..7) of that element out of it:
+//         G_ab = sum_gp g_a g_b^T,   K_ab = lambda G + mu G^T + mu tr(G) I
 //     (IsotropicLinearElasticMaterial D, isolinearelasticmaterial.C:80-84, through the B matrix of
-//     Structural3DElement::computeBmatrixAt, structural3delement.C:63-86) and parks them in shared
+//     Structural3DElement::computeBmatrixAt, structural3delement.C:63-86) and park them in shared
 //     memory at positions sorted by column.
 //   * One warp per node then sums, for each neighbouring node, the parked blocks in a fixed order,
 //     lays the node's (up to 3) rows out in shared memory and streams them to val.
@@ -24,13 +27,16 @@
 
 namespace ob200 {
 
-constexpr int kGroupVisits = 32;                     // visits per group window
+constexpr int kGroupVisits = 24;                     // visits per group window
 constexpr int kMaxValence = 16;                      // elements around a node (fast path)
 constexpr int kGatherVisits = kGroupVisits + kMaxValence;    // most visits a group can hold
-constexpr int kGatherThreads = 4 * kGroupVisits;     // 128: four lanes per visit; a group's few extra visits take a second pass
+constexpr int kGatherThreads = 128;                  // compute threads: one per (element, Gauss point), then four per visit
 constexpr int kGatherWarps = kGatherThreads / 32;
-constexpr int kMaxRowLen = 128;                      // longest row laid out in shared memory
-constexpr int kBlkDoubles = 10;                     // a parked 3x3 block, padded to 80 B (16-byte aligned)
+constexpr int kMaxRowLen = 128;                      // longest row the column-block schedule describes
+constexpr int kBlkDoubles = 10;                      // a parked 3x3 block, padded to 80 B (16-byte aligned)
+constexpr int kRoundElems = 16;                      // distinct elements whose gradients are resident at a time
+constexpr int kGpStride = 26;                        // doubles per (element, Gauss point): 24 + pad (208 B: conflict-free 16-byte stores)
+constexpr int kElStride = 8 * kGpStride + 2;         // doubles per element (1680 B: neighbouring elements land in different banks)
 
 // ---- mesh-only preprocessing (elemset create) ---------------------------------------------
 
@@ -120,6 +126,53 @@ __global__ void group_table_kernel(int32_t nnode, const int32_t *__restrict__ st
         for ( int c = lo; c <= hi; c++ ) table[c] = make_int2((int) r, start[r]);
         if ( r == nnode )
             for ( int c = ( hi + 1 > lo ? hi + 1 : lo ); c <= ngroups; c++ ) table[c] = make_int2(nnode, start[nnode]);
+    }
+}
+
+// Distinct elements of every group.  One warp per group: vu[visit] = rank of the visit's element
+// among the distinct elements of its group (ascending element number), bit 7 set on the first
+// visit of each distinct element (the producer warp builds the group's element list from those).
+__global__ void __launch_bounds__(256)
+visit_unique_kernel(int32_t ngroups, const int2 *__restrict__ gtab, const int32_t *__restrict__ ninc, unsigned char *__restrict__ vu)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    constexpr int Q = ( kGatherVisits + 31 ) / 32;
+    for ( int64_t g = warp0; g < ngroups; g += nwarps ) {
+        const int v0 = gtab[g].y, n = gtab[g + 1].y - v0;
+        int el[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            const int it = q * 32 + lane;
+            el[q] = it < n ? ( ninc[v0 + it] >> 3 ) : INT_MAX;
+        }
+        int first[Q], rank[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) { first[q] = 1; rank[q] = 0; }
+        // pass 1: first occurrence?
+        for ( int jt = 0; jt < n; jt++ ) {
+            int sel = INT_MAX;
+#pragma unroll
+            for ( int qs = 0; qs < Q; qs++ ) if ( qs == ( jt >> 5 ) ) sel = el[qs];
+            const int ej = __shfl_sync(0xffffffffu, sel, jt & 31);
+#pragma unroll
+            for ( int q = 0; q < Q; q++ ) if ( ej == el[q] && jt < q * 32 + lane ) first[q] = 0;
+        }
+        // pass 2: distinct smaller elements
+        for ( int jt = 0; jt < n; jt++ ) {
+            int sel = INT_MAX, self = 0;
+#pragma unroll
+            for ( int qs = 0; qs < Q; qs++ ) if ( qs == ( jt >> 5 ) ) { sel = el[qs]; self = first[qs]; }
+            const int ej = __shfl_sync(0xffffffffu, sel, jt & 31), fj = __shfl_sync(0xffffffffu, self, jt & 31);
+#pragma unroll
+            for ( int q = 0; q < Q; q++ ) if ( fj && ej < el[q] ) rank[q]++;
+        }
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            const int it = q * 32 + lane;
+            if ( it < n ) vu[v0 + it] = (unsigned char)( rank[q] | ( first[q] ? 0x80 : 0 ) );
+        }
     }
 }
 
@@ -269,7 +322,7 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
 
 struct GatherView {
     const int32_t *ninc_start, *ninc, *ninc_node, *nodeeq;
-    const unsigned char *pos, *nblk;
+    const unsigned char *pos, *nblk, *vu;
     const unsigned short *blk;
     const int2 *gtab;
     int maxblk;
@@ -277,16 +330,19 @@ struct GatherView {
 
 // one pipeline stage: everything phase A needs for one group, written by the producer warp
 struct GatherStage {
-    double xyz[kGatherVisits][26];        // element vertex coordinates per visit (row padded to 208 B: 16-byte rows, bank spread)
-    double lam[kGatherVisits], mu[kGatherVisits];
-    uint2 pos[kGatherVisits];             // parking positions of the 8 blocks
+    double xyz[kGatherVisits][26];        // vertex coordinates of the group's distinct elements (row padded to 208 B)
+    double lam[kGatherVisits], mu[kGatherVisits];     // per visit
+    uint2 pos[kGatherVisits];             // parking positions of the visit's 8 blocks
     int ent[kGatherVisits];               // local node index | parking base << 3
+    int uel[kGatherVisits];               // the distinct elements
+    unsigned char vu[kGatherVisits];      // visit -> index into uel
     int4 meta;                            // first node, first visit, end node, end visit
+    int nuniq;
 };
 struct GatherShared {
-    GatherStage st[2];                                         // 21,920 B
-    double park[kGatherVisits * 8 * kBlkDoubles];              // 30,720 B
-    double rows[kGatherWarps][3][kMaxRowLen];                  // 12,288 B; phase A reuses it as the quad exchange buffer [12][32]
+    GatherStage st[2];
+    double park[kGatherVisits * 8 * kBlkDoubles];
+    double grad[kRoundElems * kElStride];                      // sqrt(dV) grad N_b per (element, Gauss point)
     unsigned long long full[2], empty[2];
 };
 
@@ -311,27 +367,74 @@ __device__ __forceinline__ void mbar_wait_(unsigned long long *bar, uint32_t par
         "}\n" ::"r"( (uint32_t) __cvta_generic_to_shared(bar) ), "r"( parity ) : "memory" );
 }
 
-// 0.125 * (1 +- a)(1 +- a), a = 1/sqrt 3: the values a trilinear shape-function derivative takes at
-// the 2x2x2 Gauss points (FEI3dHexaLin::evaldNdxi, fei3dhexalin.C:129-166; gaussintegrationrule.C:1450)
-__device__ __forceinline__ double hexa_dn_pick(bool a1, bool a2)
+// Geometry of one element at one Gauss point: out[3 b + j] = sqrt(dV) dN_b/dx_j, b = 0..7.
+// FEI3dHexaLin::evaldNdxi (fei3dhexalin.C:129-166) at the 2x2x2 rule (gaussintegrationrule.C:190-214,
+// weights 1): dN_k/dxi = s_k^xi (1 + s_k^eta eta)(1 + s_k^zeta zeta) / 8, ...  Every factor takes one of
+// two values at a Gauss point, so the twelve products are formed once and each node picks its own at
+// compile time.  J = x dN/dxi, dN/dx = dN/dxi J^-1 (evaldNdx, fei3dhexalin.C:186-204); dV = |det J|
+// (Structural3DElement::computeVolumeAround, structural3delement.C:328-338).
+__device__ __forceinline__ void hexa_gradients(const double *__restrict__ xv, int gp, double *__restrict__ out)
 {
     constexpr double kA = 0.577350269189626;
-    constexpr double cPP = 0.125 * ( 1.0 + kA ) * ( 1.0 + kA ), cPM = 0.125 * ( 1.0 + kA ) * ( 1.0 - kA ),
-                     cMM = 0.125 * ( 1.0 - kA ) * ( 1.0 - kA );
-    return a1 ? ( a2 ? cPP : cPM ) : ( a2 ? cPM : cMM );
-}
-// dN_k/d(xi,eta,zeta) of node k (signs px,py,pz = "+1") at the Gauss point with signs (gu,gv,gw)
-__device__ __forceinline__ void hexa_dn_signs(bool px, bool py, bool pz, bool gu, bool gv, bool gw, double d[3])
-{
-    const bool au = px == gu, av = py == gv, aw = pz == gw;
-    const double t0 = hexa_dn_pick(av, aw), t1 = hexa_dn_pick(au, aw), t2 = hexa_dn_pick(au, av);
-    d[0] = px ? t0 : -t0;
-    d[1] = py ? t1 : -t1;
-    d[2] = pz ? t2 : -t2;
+    const bool gu = ( gp & 4 ) != 0, gv = ( gp & 2 ) != 0, gw = ( gp & 1 ) != 0;
+    // f?[1] = 1 + coordinate, f?[0] = 1 - coordinate
+    double fx[2], fy[2], fz[2];
+    fx[1] = gu ? 1.0 + kA : 1.0 - kA; fx[0] = gu ? 1.0 - kA : 1.0 + kA;
+    fy[1] = gv ? 1.0 + kA : 1.0 - kA; fy[0] = gv ? 1.0 - kA : 1.0 + kA;
+    fz[1] = gw ? 1.0 + kA : 1.0 - kA; fz[0] = gw ? 1.0 - kA : 1.0 + kA;
+    double Pyz[2][2], Pxz[2][2], Pxy[2][2];
+#pragma unroll
+    for ( int s = 0; s < 2; s++ )
+#pragma unroll
+        for ( int t = 0; t < 2; t++ ) {
+            Pyz[s][t] = 0.125 * fy[s] * fz[t];
+            Pxz[s][t] = 0.125 * fx[s] * fz[t];
+            Pxy[s][t] = 0.125 * fx[s] * fy[t];
+        }
+    double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+    const double2 *xv2 = reinterpret_cast< const double2 * >( xv );
+    double c[24];
+#pragma unroll
+    for ( int i = 0; i < 12; i++ ) {
+        const double2 v = xv2[i];
+        c[2 * i] = v.x;
+        c[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for ( int kk = 0; kk < 8; kk++ ) {
+        // signs of node kk in (xi, eta, zeta) -- the node order of FEI3dHexaLin
+        const int px = ( kk & 3 ) >= 2, py = ( ( kk & 3 ) == 1 || ( kk & 3 ) == 2 ), pz = kk < 4;
+        const double d0 = px ? Pyz[py][pz] : -Pyz[py][pz];
+        const double d1 = py ? Pxz[px][pz] : -Pxz[px][pz];
+        const double d2 = pz ? Pxy[px][py] : -Pxy[px][py];
+        const double x = c[3 * kk], y = c[3 * kk + 1], z = c[3 * kk + 2];
+        J[0][0] += x * d0; J[0][1] += x * d1; J[0][2] += x * d2;
+        J[1][0] += y * d0; J[1][1] += y * d1; J[1][2] += y * d2;
+        J[2][0] += z * d0; J[2][1] += z * d1; J[2][2] += z * d2;
+    }
+    double Ji[3][3];
+    const double sq = sqrt(fabs(inv3(J, Ji)));
+#pragma unroll
+    for ( int i = 0; i < 3; i++ )
+#pragma unroll
+        for ( int j = 0; j < 3; j++ ) Ji[i][j] *= sq;
+    double g[24];
+#pragma unroll
+    for ( int kk = 0; kk < 8; kk++ ) {
+        const int px = ( kk & 3 ) >= 2, py = ( ( kk & 3 ) == 1 || ( kk & 3 ) == 2 ), pz = kk < 4;
+        const double d0 = px ? Pyz[py][pz] : -Pyz[py][pz];
+        const double d1 = py ? Pxz[px][pz] : -Pxz[px][pz];
+        const double d2 = pz ? Pxy[px][py] : -Pxy[px][py];
+#pragma unroll
+        for ( int j = 0; j < 3; j++ ) g[3 * kk + j] = d0 * Ji[0][j] + d1 * Ji[1][j] + d2 * Ji[2][j];
+    }
+    double2 *o = reinterpret_cast< double2 * >( out );
+#pragma unroll
+    for ( int i = 0; i < 12; i++ ) o[i] = make_double2(g[2 * i], g[2 * i + 1]);
 }
 
 // Persistent, warp-specialised: warp 4 is the producer -- it walks this CTA's groups one ahead of
-// the compute warps and resolves the dependent index chain (group table -> visit -> connectivity ->
+// the compute warps and resolves the dependent index chain (group table -> visit -> element list ->
 // coordinates, material) into a shared-memory stage; warps 0-3 never wait on that chain.
 template< bool ACCUM >
 __global__ void __launch_bounds__(kGatherThreads + 32, 3)
@@ -354,25 +457,21 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
     if ( wid == kGatherWarps ) {
         // ---- producer ----
         // Software-pipelined over groups: the visit records of group k+1 (and the table entries of
-        // group k+2) are requested while the connectivity -> coordinate chain of group k resolves.
-        auto stage_visit = [&](GatherStage &st, int t, int ent, int pbase, uint2 pw, bool with_coords) {
+        // group k+2) are requested while the element -> coordinate chain of group k resolves.
+        auto stage_visit = [&](GatherStage &st, int t, int ent, int pbase, uint2 pw, int vub) {
             const int64_t e = ent >> 3;
             const MatParams *mp = S.mat + S.matid[e];
-            if ( with_coords ) {
-                const double2 *src = reinterpret_cast< const double2 * >( S.exyz + e * 24 );
-                double2 *dst = reinterpret_cast< double2 * >( st.xyz[t] );
-#pragma unroll
-                for ( int part = 0; part < 12; part++ ) dst[part] = src[part];
-            }
             double lam, mu;
             isole_lame(mp->E, mp->nu, lam, mu);
             st.lam[t] = lam;
             st.mu[t] = mu;
             st.pos[t] = pw;
             st.ent[t] = ( ent & 7 ) | ( pbase << 3 );
+            st.vu[t] = (unsigned char)( vub & 0x7F );
+            if ( vub & 0x80 ) st.uel[vub & 0x7F] = (int) e;
         };
         int2 g0 = make_int2(0, 0), g1 = g0, h0 = g0, h1 = g0;      // table entries of group k, k+1
-        int ent = 0, pbase = 0;
+        int ent = 0, pbase = 0, vub = 0;
         uint2 pw = make_uint2(0, 0);
         if ( nmine > 0 ) {
             g0 = G.gtab[blockIdx.x];
@@ -380,6 +479,7 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
             if ( lane < g1.y - g0.y ) {
                 ent = G.ninc[g0.y + lane];
                 pbase = G.ninc_node[g0.y + lane];
+                vub = G.vu[g0.y + lane];
                 pw = *reinterpret_cast< const uint2 * >( G.pos + (int64_t)( g0.y + lane ) * 8 );
             }
         }
@@ -391,11 +491,12 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
             const int s = k & 1;
             // requests for the groups behind this one
             int2 n0 = h0, n1 = h1;
-            int nent = 0, npbase = 0;
+            int nent = 0, npbase = 0, nvub = 0;
             uint2 npw = make_uint2(0, 0);
             if ( k + 1 < nmine && lane < h1.y - h0.y ) {
                 nent = G.ninc[h0.y + lane];
                 npbase = G.ninc_node[h0.y + lane];
+                nvub = G.vu[h0.y + lane];
                 npw = *reinterpret_cast< const uint2 * >( G.pos + (int64_t)( h0.y + lane ) * 8 );
             }
             if ( k + 2 < nmine ) {
@@ -406,31 +507,43 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
             if ( k >= 2 ) mbar_wait_(&sh.empty[s], ( ( k >> 1 ) - 1 ) & 1);
             GatherStage &st = sh.st[s];
             const int nvis = g1.y - g0.y;
-            // coordinates of the window's 32 visits: 12 chunks of 16 B per visit, 12 coalesced rounds
-            {
-                double2 buf[12];
-#pragma unroll
-                for ( int r = 0; r < 12; r++ ) {           // all twelve loads in flight before the first store
-                    const int c = r * 32 + lane, vis = c / 12, part = c - vis * 12;
-                    const int64_t ev = __shfl_sync(0xffffffffu, ent, vis) >> 3;
-                    buf[r] = reinterpret_cast< const double2 * >( S.exyz + ev * 24 )[part];
-                }
-#pragma unroll
-                for ( int r = 0; r < 12; r++ ) {
-                    const int c = r * 32 + lane, vis = c / 12, part = c - vis * 12;
-                    if ( vis < nvis ) reinterpret_cast< double2 * >( st.xyz[vis] )[part] = buf[r];
-                }
+            int nfirst = 0;
+            if ( lane < nvis ) {
+                stage_visit(st, lane, ent, pbase, pw, vub);
+                nfirst = ( vub >> 7 ) & 1;
             }
-            if ( lane < nvis ) stage_visit(st, lane, ent, pbase, pw, false);
-            for ( int t = lane + 32; t < nvis; t += 32 ) {           // the few visits beyond the window
+            for ( int t = lane + 32; t < nvis; t += 32 ) {           // the few visits beyond the first 32
                 const int64_t v = (int64_t) g0.y + t;
-                stage_visit(st, t, G.ninc[v], G.ninc_node[v], *reinterpret_cast< const uint2 * >( G.pos + v * 8 ), true);
+                const int vb = G.vu[v];
+                stage_visit(st, t, G.ninc[v], G.ninc_node[v], *reinterpret_cast< const uint2 * >( G.pos + v * 8 ), vb);
+                nfirst += ( vb >> 7 ) & 1;
             }
-            if ( lane == 0 ) st.meta = make_int4(g0.x, g0.y, g1.x, g1.y);
+#pragma unroll
+            for ( int o = 16; o > 0; o >>= 1 ) nfirst += __shfl_xor_sync(0xffffffffu, nfirst, o);
+            __syncwarp();
+            // coordinates of the distinct elements: 12 chunks of 16 B per element, six coalesced requests in flight per lane
+            const int nchunk = nfirst * 12;
+            for ( int c0 = 0; c0 < nchunk; c0 += 6 * 32 ) {
+                double2 buf[6];
+#pragma unroll
+                for ( int r = 0; r < 6; r++ ) {
+                    const int c = c0 + r * 32 + lane, u = c / 12, part = c - u * 12;
+                    if ( c < nchunk ) buf[r] = reinterpret_cast< const double2 * >( S.exyz + (int64_t) st.uel[u] * 24 )[part];
+                }
+#pragma unroll
+                for ( int r = 0; r < 6; r++ ) {
+                    const int c = c0 + r * 32 + lane, u = c / 12, part = c - u * 12;
+                    if ( c < nchunk ) reinterpret_cast< double2 * >( st.xyz[u] )[part] = buf[r];
+                }
+            }
+            if ( lane == 0 ) {
+                st.meta = make_int4(g0.x, g0.y, g1.x, g1.y);
+                st.nuniq = nfirst;
+            }
             __syncwarp();
             if ( lane == 0 ) mbar_arrive_(&sh.full[s]);
             g0 = h0; g1 = h1; h0 = n0; h1 = n1;
-            ent = nent; pbase = npbase; pw = npw;
+            ent = nent; pbase = npbase; pw = npw; vub = nvub;
         }
         return;
     }
@@ -442,6 +555,7 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
         mbar_wait_(&sh.full[s], ( k >> 1 ) & 1);
         const int4 meta = st.meta;
         const int n0 = meta.x, v0 = meta.y, n1 = meta.z, nvis = meta.w - meta.y;
+        const int nuniq = st.nuniq;
 
         // metadata of the node this warp will reduce first: requested now, consumed after the barrier
         int b_nb = 0, b_info = 0, b_start = 0, b_eq[3] = { 0, 0, 0 }, b_row[3] = { 0, 0, 0 };
@@ -454,108 +568,47 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
             for ( int i = 0; i < 3; i++ ) b_eq[i] = G.nodeeq[(int64_t) w * 3 + i];
         }
 
-        // ---- phase A: four lanes per visit ----
-        // Lane q of the quad inverts the Jacobian at Gauss points 2q, 2q+1 and forms dV * grad N_a there;
-        // the quad then walks the eight Gauss points, the owner broadcasts (J^-1, dV grad N_a) with
-        // shuffles, and every lane accumulates the two blocks K_ab, b = 2q, 2q+1 (18 accumulators).
-        for ( int t = tid >> 2; t < ( ( nvis + 7 ) & ~7 ); t += kGroupVisits ) {
-            const int q = tid & 3;
-            const bool live_visit = t < nvis;
-            const int tt = live_visit ? t : 0;
-            const uint2 pw = live_visit ? st.pos[tt] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-            // whole quads are live or dead together, whole warps stay converged for the shuffles
-            const bool work = !( pw.x == 0xFFFFFFFFu && pw.y == 0xFFFFFFFFu );
-            if ( !__any_sync(0xffffffffu, work) ) continue;
-            const int entw = st.ent[tt];
-            const int la = entw & 7;
-            // Jacobians of this lane's two Gauss points, 2q (w = -a) and 2q+1 (w = +a), in one sweep over
-            // the vertices (FEI3dHexaLin::evaldNdx, fei3dhexalin.C:186-204)
-            const bool qu = q >= 2, qv = ( q & 1 ) != 0;
-            double J0[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } }, J1[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
-            {
-                const double *xv = st.xyz[tt];
+        // ---- phase A, kRoundElems distinct elements at a time ----
+        for ( int r0 = 0; r0 < nuniq; r0 += kRoundElems ) {
+            const int nu = min(kRoundElems, nuniq - r0);
+            // A1: one thread per (element, Gauss point): sqrt(dV) grad N_b, b = 0..7, into shared memory
+            for ( int t = tid; t < nu * 8; t += kGatherThreads )
+                hexa_gradients(st.xyz[r0 + ( t >> 3 )], t & 7, sh.grad + ( t >> 3 ) * kElStride + ( t & 7 ) * kGpStride);
+            asm volatile( "bar.sync 1, %0;" ::"n"( kGatherThreads ) : "memory" );
+            // A2: four threads per visit; thread q contracts the blocks K_ab, b = 2q, 2q+1, over the Gauss points
+            for ( int t = tid >> 2; t < nvis; t += kGatherThreads / 4 ) {
+                const int u = (int) st.vu[t] - r0;
+                if ( (unsigned) u >= (unsigned) nu ) continue;
+                const int q = tid & 3;
+                const uint2 pw = st.pos[t];
+                const unsigned int pq = ( ( q < 2 ? pw.x : pw.y ) >> ( 16 * ( q & 1 ) ) ) & 0xFFFFu;
+                if ( pq == 0xFFFFu ) continue;              // both blocks belong to prescribed columns (or the row is prescribed)
+                const int entw = st.ent[t];
+                const int la = entw & 7;
+                const double *ge = sh.grad + u * kElStride;
+                double acc[2][9];
 #pragma unroll
-                for ( int kk = 0; kk < 8; kk++ ) {
-                    const bool px = ( kk & 3 ) >= 2, py = ( kk & 3 ) == 1 || ( kk & 3 ) == 2, pz = kk < 4;
-                    double d0[3], d1[3];
-                    hexa_dn_signs(px, py, pz, qu, qv, false, d0);
-                    hexa_dn_signs(px, py, pz, qu, qv, true, d1);
-                    const double x = xv[3 * kk], y = xv[3 * kk + 1], z = xv[3 * kk + 2];
+                for ( int bb = 0; bb < 2; bb++ )
 #pragma unroll
-                    for ( int j = 0; j < 3; j++ ) {
-                        J0[0][j] += x * d0[j]; J0[1][j] += y * d0[j]; J0[2][j] += z * d0[j];
-                        J1[0][j] += x * d1[j]; J1[1][j] += y * d1[j]; J1[2][j] += z * d1[j];
-                    }
+                    for ( int kk = 0; kk < 9; kk++ ) acc[bb][kk] = 0.0;
+#pragma unroll
+                for ( int gp = 0; gp < 8; gp++ ) {
+                    const double *gg = ge + gp * kGpStride;
+                    const double a0 = gg[3 * la], a1 = gg[3 * la + 1], a2 = gg[3 * la + 2];
+                    const double2 *gb = reinterpret_cast< const double2 * >( gg + 6 * q );
+                    const double2 b0 = gb[0], b1 = gb[1], b2 = gb[2];
+                    acc[0][0] += a0 * b0.x; acc[0][1] += a0 * b0.y; acc[0][2] += a0 * b1.x;
+                    acc[0][3] += a1 * b0.x; acc[0][4] += a1 * b0.y; acc[0][5] += a1 * b1.x;
+                    acc[0][6] += a2 * b0.x; acc[0][7] += a2 * b0.y; acc[0][8] += a2 * b1.x;
+                    acc[1][0] += a0 * b1.y; acc[1][1] += a0 * b2.x; acc[1][2] += a0 * b2.y;
+                    acc[1][3] += a1 * b1.y; acc[1][4] += a1 * b2.x; acc[1][5] += a1 * b2.y;
+                    acc[1][6] += a2 * b1.y; acc[1][7] += a2 * b2.x; acc[1][8] += a2 * b2.y;
                 }
-            }
-            const bool pxa = ( la & 3 ) >= 2, pya = ( la & 3 ) == 1 || ( la & 3 ) == 2, pza = la < 4;
-            // the two shape functions of this lane: b = 2q, 2q + 1
-            bool px[2], py[2], pz[2];
-#pragma unroll
-            for ( int bb = 0; bb < 2; bb++ ) {
-                const int b = 2 * q + bb;
-                px[bb] = ( b & 3 ) >= 2;
-                py[bb] = ( b & 3 ) == 1 || ( b & 3 ) == 2;
-                pz[bb] = b < 4;
-            }
-            double acc[2][9];
-#pragma unroll
-            for ( int bb = 0; bb < 2; bb++ )
-#pragma unroll
-                for ( int kk = 0; kk < 9; kk++ ) acc[bb][kk] = 0.0;
-            // two rounds (h = 0: the w = -a Gauss points, h = 1: w = +a): every lane inverts its Jacobian of
-            // the round, then the quad walks the four owners
-#pragma unroll
-            for ( int h = 0; h < 2; h++ ) {
-                double own[12];          // J^-1 (9), dV * grad N_a (3) at Gauss point 2q + h
-                {
-                    double Ji[3][3], da[3];
-                    const double dV = fabs(inv3(h ? J1 : J0, Ji));      // weight 1 (structural3delement.C:328-338)
-                    hexa_dn_signs(pxa, pya, pza, qu, qv, h == 1, da);
-#pragma unroll
-                    for ( int i = 0; i < 3; i++ )
-#pragma unroll
-                        for ( int j = 0; j < 3; j++ ) own[3 * i + j] = Ji[i][j];
-#pragma unroll
-                    for ( int j = 0; j < 3; j++ ) own[9 + j] = dV * ( da[0] * Ji[0][j] + da[1] * Ji[1][j] + da[2] * Ji[2][j] );
-                }
-                // publish to the quad through the warp's exchange buffer [12][32]
-                // (16-byte entries [6][4 owners][8 quads]: a read of one owner by the 8 quads is one 128-byte wavefront)
-                double2 *xch = reinterpret_cast< double2 * >( &sh.rows[wid][0][0] );
-                __syncwarp();
-#pragma unroll
-                for ( int kk = 0; kk < 6; kk++ ) xch[kk * 32 + q * 8 + ( lane >> 2 )] = make_double2(own[2 * kk], own[2 * kk + 1]);
-                __syncwarp();
-#pragma unroll 1
-                for ( int src = 0; src < 4; src++ ) {
-                    double m[12];
-#pragma unroll
-                    for ( int kk = 0; kk < 6; kk++ ) {
-                        const double2 mm = xch[kk * 32 + src * 8 + ( lane >> 2 )];
-                        m[2 * kk] = mm.x;
-                        m[2 * kk + 1] = mm.y;
-                    }
-                    const bool gu = src >= 2, gv = ( src & 1 ) != 0, gw = h == 1;     // Gauss point 2 src + h
-#pragma unroll
-                    for ( int bb = 0; bb < 2; bb++ ) {
-                        double d[3], gb[3];
-                        hexa_dn_signs(px[bb], py[bb], pz[bb], gu, gv, gw, d);
-#pragma unroll
-                        for ( int j = 0; j < 3; j++ ) gb[j] = d[0] * m[j] + d[1] * m[3 + j] + d[2] * m[6 + j];
-#pragma unroll
-                        for ( int i = 0; i < 3; i++ )
-#pragma unroll
-                            for ( int j = 0; j < 3; j++ ) acc[bb][3 * i + j] += m[9 + i] * gb[j];
-                    }
-                }
-            }
-            if ( work ) {
-                const double lam = st.lam[tt], mu = st.mu[tt];
+                const double lam = st.lam[t], mu = st.mu[t];
                 const int base = entw >> 3;
-                const unsigned int pq = q < 2 ? pw.x : pw.y;
 #pragma unroll
                 for ( int bb = 0; bb < 2; bb++ ) {
-                    const unsigned int p = ( pq >> ( 16 * ( q & 1 ) + 8 * bb ) ) & 0xFFu;
+                    const unsigned int p = ( pq >> ( 8 * bb ) ) & 0xFFu;
                     if ( p == 0xFFu ) continue;
                     const double *g = acc[bb];
                     const double tr = mu * ( g[0] + g[4] + g[8] );
@@ -567,6 +620,7 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
                     o[4].x = lam * g[8] + mu * g[8] + tr;
                 }
             }
+            if ( r0 + kRoundElems < nuniq ) asm volatile( "bar.sync 1, %0;" ::"n"( kGatherThreads ) : "memory" );
         }
         // second level of the phase-B metadata (its address arrived during phase A)
 #pragma unroll
@@ -683,6 +737,9 @@ int gather_prepare_mesh(ob200_elemset *S)
     OB_CHECK( S->gtab.alloc(S->ngroups + 1) );
     OB_LAUNCH(ctx, group_table_kernel, ctx->shape.grid(S->nnode + 1, 256, 8), 256, 0, (int32_t) S->nnode, S->ninc_start.p, S->ngroups, S->gtab.p);
     OB_LAUNCH(ctx, visit_base_kernel, ctx->shape.grid(S->nnode, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->gtab.p, S->ninc_node.p);
+    OB_CHECK( S->vu.alloc(n) );
+    if ( S->maxval <= kMaxValence )
+        OB_LAUNCH(ctx, visit_unique_kernel, ctx->shape.grid((int64_t) S->ngroups * 32, 256, 8), 256, 0, S->ngroups, S->gtab.p, S->ninc.p, S->vu.p);
     OB_CHECK( S->exyz.alloc(n * 3) );
     OB_LAUNCH(ctx, element_coords_kernel, grid, 256, 0, S->conn.p, S->coords.p, n, S->exyz.p);
     OB_CHECK( S->nodeeq.alloc(S->nnode * 3) );
@@ -731,7 +788,7 @@ int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A)
         OB_CUDA( cudaFuncSetAttribute(lspace_gather_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
         attr_set = true;
     }
-    GatherView G{ S->ninc_start.p, S->ninc.p, S->ninc_node.p, S->nodeeq.p, S->pos.p, S->nblk.p, S->blk.p, S->gtab.p, S->maxblk };
+    GatherView G{ S->ninc_start.p, S->ninc.p, S->ninc_node.p, S->nodeeq.p, S->pos.p, S->nblk.p, S->vu.p, S->blk.p, S->gtab.p, S->maxblk };
     ElemSetView v = S->view();
     int grid = ctx->shape.sms * 3;                     // persistent: 3 CTAs per SM
     if ( grid > S->ngroups ) grid = S->ngroups;

@@ -58,7 +58,7 @@ struct ob200_elemset {
     // ... and what depends on the bound matrix
     bool gather_ok = false, covers_all = false;
     int32_t maxblk = 0, ngroups = 0;
-    ob200::DevBuf< unsigned char > pos, nblk;
+    ob200::DevBuf< unsigned char > pos, nblk, vu;
     ob200::DevBuf< unsigned short > blk;
     ob200::DevBuf< int2 > gtab;
     bool all_isole = true;
