@@ -29,7 +29,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for s in SOURCES:
         o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc, "-c", os.path.join(CSRC, s), "-o", o] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+        cmd = ([nvcc, "-c", os.path.join(CSRC, s), "-o", o] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+               + os.environ.get("OB200_EXTRA_NVCC", "").split())
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     fail = False

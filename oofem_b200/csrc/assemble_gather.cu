@@ -27,14 +27,23 @@
 
 namespace ob200 {
 
-constexpr int kGroupVisits = 24;                     // visits per group window
+#ifndef OB200_GROUP_VISITS
+#define OB200_GROUP_VISITS 24
+#endif
+#ifndef OB200_ROUND_ELEMS
+#define OB200_ROUND_ELEMS 16
+#endif
+#ifndef OB200_GATHER_CTAS
+#define OB200_GATHER_CTAS 3
+#endif
+constexpr int kGroupVisits = OB200_GROUP_VISITS;     // visits per group window
 constexpr int kMaxValence = 16;                      // elements around a node (fast path)
 constexpr int kGatherVisits = kGroupVisits + kMaxValence;    // most visits a group can hold
 constexpr int kGatherThreads = 128;                  // compute threads: one per (element, Gauss point), then four per visit
 constexpr int kGatherWarps = kGatherThreads / 32;
 constexpr int kMaxRowLen = 128;                      // longest row the column-block schedule describes
 constexpr int kBlkDoubles = 10;                      // a parked 3x3 block, padded to 80 B (16-byte aligned)
-constexpr int kRoundElems = 16;                      // distinct elements whose gradients are resident at a time
+constexpr int kRoundElems = OB200_ROUND_ELEMS;                    // distinct elements whose gradients are resident at a time
 constexpr int kGpStride = 26;                        // doubles per (element, Gauss point): 24 + pad (208 B: conflict-free 16-byte stores)
 constexpr int kElStride = 8 * kGpStride + 2;         // doubles per element (1680 B: neighbouring elements land in different banks)
 
@@ -354,6 +363,22 @@ __device__ __forceinline__ void mbar_arrive_(unsigned long long *bar)
 {
     asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( (uint32_t) __cvta_generic_to_shared(bar) ) : "memory" );
 }
+// the producer's wait: it runs a whole group ahead, so it polls with a back-off instead of taking issue
+// slots from the compute warps
+__device__ __forceinline__ void mbar_wait_relaxed_(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for ( ;; ) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"( done ) : "r"( (uint32_t) __cvta_generic_to_shared(bar) ), "r"( parity ) : "memory" );
+        if ( done ) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void mbar_wait_(unsigned long long *bar, uint32_t parity)
 {
     asm volatile(
@@ -437,7 +462,7 @@ __device__ __forceinline__ void hexa_gradients(const double *__restrict__ xv, in
 // the compute warps and resolves the dependent index chain (group table -> visit -> element list ->
 // coordinates, material) into a shared-memory stage; warps 0-3 never wait on that chain.
 template< bool ACCUM >
-__global__ void __launch_bounds__(kGatherThreads + 32, 3)
+__global__ void __launch_bounds__(kGatherThreads + 32, OB200_GATHER_CTAS)
 lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t *__restrict__ rowptr, double *__restrict__ val)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -504,7 +529,7 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
                 n0 = G.gtab[g];
                 n1 = G.gtab[g + 1];
             }
-            if ( k >= 2 ) mbar_wait_(&sh.empty[s], ( ( k >> 1 ) - 1 ) & 1);
+            if ( k >= 2 ) mbar_wait_relaxed_(&sh.empty[s], ( ( k >> 1 ) - 1 ) & 1);
             GatherStage &st = sh.st[s];
             const int nvis = g1.y - g0.y;
             int nfirst = 0;
@@ -790,7 +815,7 @@ int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A)
     }
     GatherView G{ S->ninc_start.p, S->ninc.p, S->ninc_node.p, S->nodeeq.p, S->pos.p, S->nblk.p, S->vu.p, S->blk.p, S->gtab.p, S->maxblk };
     ElemSetView v = S->view();
-    int grid = ctx->shape.sms * 3;                     // persistent: 3 CTAs per SM
+    int grid = ctx->shape.sms * OB200_GATHER_CTAS;     // persistent: as many CTAs as fit an SM
     if ( grid > S->ngroups ) grid = S->ngroups;
     if ( A->zero_pending && !S->covers_all ) OB_CHECK( ob200_csr_materialize(A) );
     if ( A->zero_pending ) {

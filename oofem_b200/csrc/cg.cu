@@ -409,12 +409,14 @@ extern "C" {
 int ob200_cg_solve(ob200_csr *A, const double *b, double *x, int precond, int max_iter, double tol, int *iters,
                    double *resid, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     return cg_entry(A, nullptr, b, x, precond, max_iter, tol, iters, resid, on_device);
 }
 
 int ob200_cg_solve_dist(ob200_csr *A, ob200_comm *c, const double *b, double *x, int precond, int max_iter, double tol,
                         int *iters, double *resid, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(c, OB200_EINVAL, "cg_solve_dist: null communicator");
     OB_REQUIRE(c->neq == ( A ? A->neq : 0 ), OB200_EINVAL, "cg_solve_dist: halo describes %d equations, matrix has %d", c->neq, A ? A->neq : 0);
     return cg_entry(A, c, b, x, precond, max_iter, tol, iters, resid, on_device);

@@ -134,6 +134,7 @@ int ob200_comm_unique_id(void *id128)
 
 int ob200_comm_create(ob200_context *ctx, int nranks, int rank, const void *id128, ob200_comm **out)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && out && nranks >= 1 && rank >= 0 && rank < nranks, OB200_EINVAL, "comm_create: bad argument");
     ob200_comm *c = new ob200_comm();
     c->ctx = ctx;
@@ -172,6 +173,7 @@ void ob200_comm_destroy(ob200_comm *c)
 int ob200_comm_set_halo(ob200_comm *c, int32_t neq, int nneigh, const int32_t *neigh_rank, const int64_t *neigh_offset,
                         const int32_t *shared_eq, const uint8_t *owned)
 {
+    if ( c ) ob200::bind_stream(c->ctx);
     OB_REQUIRE(c && neq >= 0 && nneigh >= 0, OB200_EINVAL, "comm_set_halo: bad argument");
     OB_REQUIRE(nneigh == 0 || ( neigh_rank && neigh_offset && shared_eq ), OB200_EINVAL, "comm_set_halo: null halo arrays");
     ob200_context *ctx = c->ctx;
@@ -228,6 +230,7 @@ int ob200_comm_set_halo(ob200_comm *c, int32_t neq, int nneigh, const int32_t *n
 
 int ob200_comm_exchange_add(ob200_comm *c, double *y_dev)
 {
+    if ( c ) ob200::bind_stream(c->ctx);
     OB_REQUIRE(c && y_dev, OB200_EINVAL, "comm_exchange_add: null argument");
     return comm_exchange_add(c, y_dev);
 }

@@ -51,21 +51,40 @@ struct LaunchShape {
     }
 };
 
-// simple owning device buffer
+// The stream of the context the calling thread is working for.  Every C-ABI entry point binds it
+// (bind_stream) before touching device memory: DevBuf allocations are stream-ordered on it.
+struct StreamSlot { cudaStream_t stream = nullptr; };
+StreamSlot &current_stream();
+bool stream_alive(cudaStream_t s);          // false once the owning context has been destroyed
+
+// simple owning device buffer.  Stream-ordered (cudaMallocAsync from the device's default pool, whose
+// release threshold context_create raises so that freed blocks stay cached): creating and dropping
+// work buffers inside a call costs no cudaMalloc/cudaFree device synchronisation.
 template< class T >
 struct DevBuf {
     T *p = nullptr;
     int64_t n = 0;
+    cudaStream_t s = nullptr;
     int alloc(int64_t count)
     {
         release();
         n = count;
-        if ( count > 0 ) OB_CUDA( cudaMalloc(&p, sizeof( T ) * (size_t) count) );
+        s = current_stream().stream;
+        if ( count > 0 ) {
+            if ( stream_alive(s) ) OB_CUDA( cudaMallocAsync(&p, sizeof( T ) * (size_t) count, s) );
+            else OB_CUDA( cudaMalloc(&p, sizeof( T ) * (size_t) count) );
+        }
         return OB200_OK;
     }
     void release()
     {
-        if ( p ) cudaFree(p);
+        if ( p ) {
+            // an object that outlives its context frees synchronously
+            if ( !stream_alive(s) || cudaFreeAsync(p, s) != cudaSuccess ) {
+                cudaGetLastError();
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         n = 0;
     }
@@ -106,6 +125,10 @@ struct ob200_context {
     // reduction scratch (partials) and small device scalars, used by CG
     ob200::DevBuf< double > partials;
 };
+
+namespace ob200 {
+inline void bind_stream(ob200_context *ctx) { current_stream().stream = ctx->stream; }
+}
 
 #define OB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
     do {                                                                                 \

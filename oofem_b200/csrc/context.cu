@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
+#include <set>
 
 namespace ob200 {
 static thread_local char g_err[1024] = "";
@@ -11,6 +13,26 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof( g_err ), fmt, ap);
     va_end(ap);
+}
+
+StreamSlot &current_stream()
+{
+    static thread_local StreamSlot slot;
+    return slot;
+}
+
+static std::mutex g_streams_mu;
+static std::set< cudaStream_t > g_streams;
+bool stream_alive(cudaStream_t s)
+{
+    std::lock_guard< std::mutex > lk(g_streams_mu);
+    return g_streams.count(s) != 0;
+}
+static void stream_register(cudaStream_t s, bool alive)
+{
+    std::lock_guard< std::mutex > lk(g_streams_mu);
+    if ( alive ) g_streams.insert(s);
+    else g_streams.erase(s);
 }
 
 __global__ void flush_kernel(char *p, int64_t n, char v)
@@ -49,6 +71,15 @@ int ob200_context_create(int device, ob200_context **out)
         return OB200_ECUDA;
     }
     ctx->shape.sms = ctx->prop.multiProcessorCount;
+    // keep freed work buffers cached in the pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if ( cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess ) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    stream_register(ctx->stream, true);
+    ob200::bind_stream(ctx);
     *out = ctx;
     return OB200_OK;
 }
@@ -60,12 +91,16 @@ void ob200_context_destroy(ob200_context *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->flush.release();
     ctx->partials.release();
+    cudaStreamSynchronize(ctx->stream);
+    stream_register(ctx->stream, false);
+    if ( current_stream().stream == ctx->stream ) current_stream().stream = nullptr;
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int ob200_context_sync(ob200_context *ctx)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx, OB200_EINVAL, "context_sync: null context");
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
     return OB200_OK;
@@ -76,6 +111,7 @@ int64_t ob200_context_launch_count(ob200_context *ctx) { return ctx ? ctx->launc
 
 int ob200_context_set_profiling(ob200_context *ctx, int enable)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx, OB200_EINVAL, "set_profiling: null context");
     ctx->profiling = enable != 0;
     return OB200_OK;
@@ -99,6 +135,7 @@ static int profile_fold(ob200_context *ctx)
 
 int ob200_context_profile_reset(ob200_context *ctx)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx, OB200_EINVAL, "profile_reset: null context");
     OB_CHECK( profile_fold(ctx) );
     ctx->prof_total.clear();
@@ -107,6 +144,7 @@ int ob200_context_profile_reset(ob200_context *ctx)
 
 int ob200_context_profile_report(ob200_context *ctx, char *buf, int64_t buflen)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && buf && buflen > 0, OB200_EINVAL, "profile_report: bad argument");
     OB_CHECK( profile_fold(ctx) );
     std::string out;
@@ -122,6 +160,7 @@ int ob200_context_profile_report(ob200_context *ctx, char *buf, int64_t buflen)
 
 int ob200_malloc(ob200_context *ctx, int64_t bytes, void **dptr)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && dptr && bytes >= 0, OB200_EINVAL, "malloc: bad argument");
     OB_CUDA( cudaSetDevice(ctx->device) );
     *dptr = nullptr;
@@ -131,6 +170,7 @@ int ob200_malloc(ob200_context *ctx, int64_t bytes, void **dptr)
 
 int ob200_free(ob200_context *ctx, void *dptr)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx, OB200_EINVAL, "free: null context");
     if ( dptr ) {
         OB_CUDA( cudaStreamSynchronize(ctx->stream) );
@@ -141,6 +181,7 @@ int ob200_free(ob200_context *ctx, void *dptr)
 
 int ob200_memcpy_h2d(ob200_context *ctx, void *dst, const void *src, int64_t bytes)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && ( bytes == 0 || ( dst && src ) ), OB200_EINVAL, "memcpy_h2d: bad argument");
     if ( bytes ) OB_CUDA( cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyHostToDevice, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
@@ -149,6 +190,7 @@ int ob200_memcpy_h2d(ob200_context *ctx, void *dst, const void *src, int64_t byt
 
 int ob200_memcpy_d2h(ob200_context *ctx, void *dst, const void *src, int64_t bytes)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && ( bytes == 0 || ( dst && src ) ), OB200_EINVAL, "memcpy_d2h: bad argument");
     if ( bytes ) OB_CUDA( cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyDeviceToHost, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
@@ -157,6 +199,7 @@ int ob200_memcpy_d2h(ob200_context *ctx, void *dst, const void *src, int64_t byt
 
 int ob200_memset(ob200_context *ctx, void *dst, int value, int64_t bytes)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && ( bytes == 0 || dst ), OB200_EINVAL, "memset: bad argument");
     if ( bytes ) OB_CUDA( cudaMemsetAsync(dst, value, (size_t) bytes, ctx->stream) );
     return OB200_OK;
@@ -164,6 +207,7 @@ int ob200_memset(ob200_context *ctx, void *dst, int value, int64_t bytes)
 
 int ob200_flush_l2(ob200_context *ctx)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx, OB200_EINVAL, "flush_l2: null context");
     const int64_t bytes = (int64_t) 256 << 20;        // 256 MiB > 126 MB L2
     if ( !ctx->flush.p ) OB_CHECK( ctx->flush.alloc(bytes) );

@@ -185,6 +185,7 @@ void ob200_csr_touch(ob200_csr *A) { A->version++; }
 
 int ob200_csr_materialize(ob200_csr *A)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     if ( A->zero_pending ) {
         if ( A->nnz ) OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t) A->nnz, A->ctx->stream) );
         A->zero_pending = false;
@@ -248,6 +249,7 @@ extern "C" {
 
 int ob200_csr_create(ob200_context *ctx, ob200_csr **out)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && out, OB200_EINVAL, "csr_create: null argument");
     ob200_csr *A = new ob200_csr();
     A->ctx = ctx;
@@ -263,6 +265,7 @@ int64_t ob200_csr_version(const ob200_csr *A) { return A ? A->version : 0; }
 
 int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t nd, const int32_t *loc, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && ( loc || nelem == 0 ), OB200_EINVAL, "csr_build_structure: null argument");
     OB_REQUIRE(neq >= 0 && nelem >= 0 && nd > 0, OB200_EINVAL, "csr_build_structure: bad sizes neq=%d nelem=%lld nd=%d", neq, (long long) nelem, nd);
     ob200_context *ctx = A->ctx;
@@ -347,6 +350,7 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
 
 int ob200_csr_get_structure(const ob200_csr *A, int32_t *rowptr, int32_t *colind, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && rowptr && colind, OB200_EINVAL, "csr_get_structure: null argument");
     OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "csr_get_structure: matrix has no structure");
     cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -358,6 +362,7 @@ int ob200_csr_get_structure(const ob200_csr *A, int32_t *rowptr, int32_t *colind
 
 int ob200_csr_get_values(const ob200_csr *A, double *val, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && val, OB200_EINVAL, "csr_get_values: null argument");
     OB_CHECK( ob200_csr_materialize(const_cast< ob200_csr * >( A )) );
     if ( A->nnz )
@@ -369,6 +374,7 @@ int ob200_csr_get_values(const ob200_csr *A, double *val, int on_device)
 
 int ob200_csr_set_values(ob200_csr *A, const double *val, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && val, OB200_EINVAL, "csr_set_values: null argument");
     A->zero_pending = false;
     if ( A->nnz )
@@ -381,6 +387,7 @@ int ob200_csr_set_values(ob200_csr *A, const double *val, int on_device)
 
 int ob200_csr_device_arrays(ob200_csr *A, const int32_t **rowptr, const int32_t **colind, double **val)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A, OB200_EINVAL, "csr_device_arrays: null matrix");
     OB_CHECK( ob200_csr_materialize(A) );
     if ( rowptr ) *rowptr = A->rowptr.p;
@@ -391,6 +398,7 @@ int ob200_csr_device_arrays(ob200_csr *A, const int32_t **rowptr, const int32_t 
 
 int ob200_csr_zero(ob200_csr *A)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A, OB200_EINVAL, "csr_zero: null matrix");
     A->zero_pending = true;         // performed by the next reader / partial writer, absorbed by a full overwrite
     A->version++;
@@ -399,6 +407,7 @@ int ob200_csr_zero(ob200_csr *A)
 
 int ob200_csr_scale(ob200_csr *A, double s)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A, OB200_EINVAL, "csr_scale: null matrix");
     OB_CHECK( ob200_csr_materialize(A) );
     if ( A->nnz ) {
@@ -411,6 +420,7 @@ int ob200_csr_scale(ob200_csr *A, double s)
 
 int ob200_csr_assemble(ob200_csr *A, int64_t nelem, int32_t nd, const int32_t *loc, const double *mat, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && ( nelem == 0 || ( loc && mat ) ), OB200_EINVAL, "csr_assemble: null argument");
     OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "csr_assemble: matrix has no structure");
     OB_REQUIRE(nd > 0 && nelem >= 0, OB200_EINVAL, "csr_assemble: dimension of 'k' and 'loc' mismatch");
@@ -436,6 +446,7 @@ int ob200_csr_assemble(ob200_csr *A, int64_t nelem, int32_t nd, const int32_t *l
 
 int ob200_csr_times(ob200_csr *A, const double *x, double *y, int on_device)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && ( A->neq == 0 || ( x && y ) ), OB200_EINVAL, "csr_times: null argument");
     Staged< double > X;
     StagedOut< double > Y;
@@ -447,6 +458,7 @@ int ob200_csr_times(ob200_csr *A, const double *x, double *y, int on_device)
 
 int ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value)
 {
+    if ( A ) ob200::bind_stream(A->ctx);
     OB_REQUIRE(A && value, OB200_EINVAL, "csr_at: null argument");
     // CompCol::at (compcol.C:376-390): "Array accessing exception -- out of bounds"
     OB_REQUIRE(i >= 1 && j >= 1 && i <= A->neq && j <= A->neq, OB200_EINVAL, "csr_at: (%d,%d) out of bounds", i, j);

@@ -392,6 +392,7 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
                          const int32_t *conn, const int32_t *matid, int32_t nmat, const double *matparams,
                          const int32_t *loc, int32_t neq, int on_device, ob200_elemset **out)
 {
+    if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && out, OB200_EINVAL, "elemset_create: null context/out");
     OB_REQUIRE(etype == OB200_LSPACE || etype == OB200_LTRSPACE, OB200_EINVAL, "elemset_create: unknown element type %d", etype);
     OB_REQUIRE(nnode >= 0 && nelem >= 0 && nmat >= 1, OB200_EINVAL, "elemset_create: negative size or no material");
@@ -458,6 +459,7 @@ int64_t ob200_elemset_size(const ob200_elemset *S) { return S ? S->nelem : 0; }
 
 int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && Ke, OB200_EINVAL, "elemset_stiffness: null argument");
     StagedOut< double > o;
     OB_CHECK( o.stage(S->ctx, Ke, S->nelem * S->nd * S->nd, on_device) );
@@ -467,6 +469,7 @@ int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
 
 int ob200_elemset_internal_forces(ob200_elemset *S, const double *u, double *fe, double *gp_strain, double *gp_stress, int on_device)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && u && fe, OB200_EINVAL, "elemset_internal_forces: null argument");
     Staged< double > du;
     StagedOut< double > of, oe, os;
@@ -504,6 +507,7 @@ static int build_slot_map(ob200_elemset *S, ob200_csr *A)
 
 int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && A, OB200_EINVAL, "elemset_bind: null argument");
     OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "elemset_bind: matrix has no structure (call ob200_csr_build_structure first)");
     S->bound = nullptr;
@@ -519,6 +523,7 @@ int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
 
 int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && A, OB200_EINVAL, "elemset_assemble_stiffness: null argument");
     if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
     if ( S->gather_ok ) {
@@ -535,6 +540,7 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
 
 int ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, double *f, double *ebe_norm2, int on_device)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && u && f, OB200_EINVAL, "elemset_assemble_internal_forces: null argument");
     Staged< double > du;
     StagedOut< double > of;
@@ -555,6 +561,7 @@ int ob200_elemset_assemble_internal_forces(ob200_elemset *S, const double *u, do
 
 int ob200_elemset_assemble_extrapolated_forces(ob200_elemset *S, const double *du, double *f, int on_device)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && du && f, OB200_EINVAL, "elemset_assemble_extrapolated_forces: null argument");
     Staged< double > d;
     StagedOut< double > of;
@@ -566,6 +573,7 @@ int ob200_elemset_assemble_extrapolated_forces(ob200_elemset *S, const double *d
 
 int ob200_elemset_commit(ob200_elemset *S)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S, OB200_EINVAL, "elemset_commit: null argument");
     if ( !S->has_state ) return OB200_OK;
     int64_t n = S->nelem * S->ngp;
@@ -575,6 +583,7 @@ int ob200_elemset_commit(ob200_elemset *S)
 
 int ob200_elemset_get_state(ob200_elemset *S, double *state, int on_device)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && state, OB200_EINVAL, "elemset_get_state: null argument");
     OB_REQUIRE(S->has_state, OB200_EINVAL, "elemset_get_state: element set has no MisesMat state");
     OB_CUDA( cudaMemcpyAsync(state, S->state.p, sizeof( double ) * (size_t) S->state.n,
@@ -585,6 +594,7 @@ int ob200_elemset_get_state(ob200_elemset *S, double *state, int on_device)
 
 int ob200_elemset_set_state(ob200_elemset *S, const double *state, int on_device)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && state, OB200_EINVAL, "elemset_set_state: null argument");
     OB_REQUIRE(S->has_state, OB200_EINVAL, "elemset_set_state: element set has no MisesMat state");
     OB_CUDA( cudaMemcpyAsync(S->state.p, state, sizeof( double ) * (size_t) S->state.n,
@@ -623,6 +633,7 @@ __global__ void __launch_bounds__(256) probe_scatter_kernel(const int32_t *__res
 }
 extern "C" int ob200_debug_probe_scatter(ob200_elemset *S, ob200_csr *A, int mode, int blocks_per_sm)
 {
+    if ( S ) ob200::bind_stream(S->ctx);
     if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
     OB_CHECK( build_slot_map(S, A) );
     const int32_t *rowptr, *colind;
