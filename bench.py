@@ -222,6 +222,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: native libraries that print there (NCCL's version banner)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
@@ -414,7 +419,8 @@ def run_ours(args):
                                 "cores": cpu.get("threads", 1), "kind": kind,
                                 "sample": f"{cpu['nelem']} LSpace elements (40x20x20 sample of the same beam) assembled by the "
                                           f"reference's EngngModel::assemble into CompCol; 20 IML CG iterations at nnz {cpu['nnz']}"}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist:
         dist.barrier()
         dist.destroy_process_group()
