@@ -357,7 +357,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------
     peak, peak_src = load_peaks()
-    spmv_name = "spmv_stream_kernel< true >" if world == 1 else "spmv_stream_kernel< false >"
+    # the CG product: fused p.q on one GPU (< 1 >), fused p.q + halo push over peer memory (< 2 >), plain (< 0 >, NCCL)
+    spmv_name = max(("spmv_stream_kernel< 1 >", "spmv_stream_kernel< 2 >", "spmv_stream_kernel< 0 >"),
+                    key=lambda k: prof.get(k, (0.0, 0))[0])
     asm_name = next((k for k in ("lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
                                  "lspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_gather_kernel< false >")
     ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
@@ -399,6 +401,7 @@ def run_ours(args):
                                f"cantilever per GPU, FP64 PCG (BASELINE.json configs[1])",
                    "nelem_per_gpu": nelem, "neq_per_gpu": neq, "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
                    "precond": "diag", "partition": f"{world} x-slabs, shared-plane halo" if world > 1 else "none",
+                   "transport": ("peer memory (CUDA IPC mailboxes over NVLink)" if comm.p2p else "NCCL") if comm else "none",
                    "l2": "inputs larger than L2 (val+colind ~3 GB per pass vs 126 MB L2), no flush needed",
                    "structure_build_s": round(t_structure, 4)},
         "roofline": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",

@@ -165,6 +165,14 @@ void ob200_comm_destroy(ob200_comm *c);
 int  ob200_comm_set_halo(ob200_comm *c, int32_t neq, int nneigh, const int32_t *neigh_rank,
                          const int64_t *neigh_offset /* [nneigh+1] */, const int32_t *shared_eq,
                          const uint8_t *owned);
+/* Peer-memory transport for the ranks of one NVLink/NVSwitch node (optional; NCCL is used without it):
+ * every rank exports a mailbox in its HBM as a 64-byte CUDA IPC handle (cap = most dofs any two
+ * ranks share), the caller gathers the handles of all ranks (torch.distributed / MPI_Allgather, as
+ * OOFEM's ProblemCommunicator would) and hands the nranks x 64 bytes to _open.  From then on the
+ * halo sum and the CG reductions are written straight into the peers' memory by the kernels. */
+int  ob200_comm_p2p_export(ob200_comm *c, int64_t cap, void *handle64);
+int  ob200_comm_p2p_open(ob200_comm *c, const void *handles);
+int  ob200_comm_p2p_enabled(const ob200_comm *c);
 /* y <- y + contributions of the neighbours for shared dofs (OOFEM: updateSharedDofManagers) */
 int  ob200_comm_exchange_add(ob200_comm *c, double *y_dev);
 /* distributed PCG: A is the local sub-assembled matrix of this partition, b must already

@@ -5,6 +5,7 @@ unique id is created by rank 0 and handed round by the caller's own process grou
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -47,7 +48,44 @@ class Comm:
         owned = np.ascontiguousarray(owned, dtype=np.uint8)
         check(lib().ob200_comm_set_halo(self.h, int(neq), int(neigh_rank.size), ptr(neigh_rank), ptr(neigh_offset),
                                         ptr(shared_eq), ptr(owned)))
+        if self.nranks > 1 and os.environ.get("OB200_P2P", "1") != "0":
+            self.enable_p2p(int(np.diff(neigh_offset).max()) if neigh_rank.size else 0)
         return self
+
+    def enable_p2p(self, pair_count: int) -> bool:
+        """Map the mailboxes of all ranks of the node (CUDA IPC over the initialised torch.distributed
+        group) so that the halo sum and the CG reductions go through peer memory instead of NCCL.
+        Collective: every rank must call it.  Returns False (NCCL stays in use) if any rank cannot map."""
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() != self.nranks:
+            return False
+        dev = torch.device("cuda", torch.cuda.current_device())
+        cap = torch.tensor([pair_count], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        handle = (C.c_char * 64)()
+        ok = lib().ob200_comm_p2p_export(self.h, int(cap.item()), handle) == 0
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).clone().to(dev)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(self.nranks)]
+        dist.all_gather(allh, mine)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return False
+        raw = b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
+        buf = (C.c_char * len(raw)).from_buffer_copy(raw)
+        rc = lib().ob200_comm_p2p_open(self.h, buf)
+        flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            # some rank could not map: nobody may use the mailboxes
+            raise RuntimeError("peer-memory transport could not be mapped on every rank; set OB200_P2P=0 to use NCCL: "
+                               + lib().ob200_last_error().decode())
+        return True
+
+    @property
+    def p2p(self) -> bool:
+        return bool(lib().ob200_comm_p2p_enabled(self.h))
 
     def exchange_add(self, y_dev):
         """y <- y + the neighbours' contributions on shared dofs (device vector, in place)."""

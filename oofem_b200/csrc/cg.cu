@@ -11,11 +11,15 @@
 #include "common.cuh"
 #include "elemset.h"
 #include "comm.h"
+#include "spmv_halo.h"
+#include <stdlib.h>
 
 namespace ob200 {
 
 int spmv(ob200_csr *A, const double *x, double *y);
 int spmv_fused_dot(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done);
+bool spmv_halo_supported(const ob200_csr *A);
+int spmv_fused_halo(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done, const SpmvHalo &halo);
 
 struct CgScalars {
     double normb, rho, rho_1, alpha, beta, resid;
@@ -281,6 +285,64 @@ __global__ void cg_scalars_kernel(int stage, int iter, double tol, const double 
     cg_scalars(stage, iter, tol, red, S);
 }
 
+// distributed path over peer memory (comm_p2p.cu): all-gather of the locally reduced sums through the
+// mailboxes, summed in rank order by every rank (bit-identical everywhere), then the scalar update --
+// replaces ncclAllReduce + cg_scalars_kernel.  nA + nB > 0: red[0] is first formed from the per-CTA
+// partial sums of the fused SpMV (pa) and of the halo pull (pb) in a fixed order.  Lane r of warp 0
+// talks to rank r; a value travels as two self-validating words (spmv_halo.h: ll_store).
+__global__ void __launch_bounds__(kCgThreads)
+cg_scalars_p2p_kernel(int stage, int iter, double tol, double *__restrict__ red, int nred, CgScalars *S, int nranks,
+                      const double *__restrict__ pa, int nA, const double *__restrict__ pb, int nB,
+                      unsigned long long *const *__restrict__ peer_sdata, const unsigned long long *own_sdata,
+                      int64_t half_words, unsigned int seq, int *error)
+{
+    __shared__ double scratch[32];
+    if ( S->done ) return;
+    if ( nA + nB > 0 ) {
+        const double a = sum_partials(pa, nA, scratch);
+        __syncthreads();
+        const double b = sum_partials(pb, nB, scratch);
+        if ( threadIdx.x == 0 ) red[0] = a + b;
+        __syncthreads();
+    }
+    if ( threadIdx.x >= 32 ) return;
+    const int lane = threadIdx.x;
+    if ( lane < nranks )
+        for ( int j = 0; j < nred; j++ ) ll_store(peer_sdata[lane] + half_words + 2 * j, red[j], seq);
+    double v[kRedMax] = { 0.0, 0.0, 0.0 };
+    bool ok = true;
+    if ( lane < nranks ) {
+        unsigned long long t0 = 0, t1;
+        for ( int j = 0; j < nred && ok; j++ ) {
+            const unsigned long long *slot = own_sdata + half_words + 2 * ( (int64_t) lane * 4 + j );
+            unsigned long long w0, w1;
+            for ( int spin = 0;; spin++ ) {
+                asm volatile( "ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"( w0 ), "=l"( w1 ) : "l"( slot ) : "memory" );
+                if ( (unsigned int)( w0 >> 32 ) == seq && (unsigned int)( w1 >> 32 ) == seq ) break;
+                if ( spin == 64 ) asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t0 ) );
+                if ( spin > 64 ) {
+                    asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t1 ) );
+                    if ( t1 - t0 > 4000000000ull ) { ok = false; break; }
+                    __nanosleep(32);
+                }
+            }
+            v[j] = __longlong_as_double((long long)( ( w0 & 0xffffffffull ) | ( w1 << 32 ) ));
+        }
+    }
+    if ( !__all_sync(0xffffffffu, ok) ) {
+        if ( lane == 0 ) { atomicExch(error, 1); S->done = 1; }
+        return;
+    }
+    double tot[kRedMax] = { 0.0, 0.0, 0.0 };
+    for ( int r = 0; r < nranks; r++ )
+#pragma unroll
+        for ( int j = 0; j < kRedMax; j++ ) tot[j] += __shfl_sync(0xffffffffu, v[j], r);
+    if ( lane == 0 ) {
+        for ( int j = 0; j < nred; j++ ) red[j] = tot[j];
+        cg_scalars(stage, iter, tol, tot, S);
+    }
+}
+
 struct CgWork {
     double *r, *p, *q, *partials, *red;
     CgScalars *S;
@@ -336,8 +398,20 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
     }
 
     // distributed: all-reduce the locally reduced sums, then the scalar update in its own launch
-    auto finish = [&](int stage, int iter, int nred) -> int {
+    const bool p2p = dist && comm->p2p;
+    static const bool allow_fused = !( getenv("OB200_FUSED_HALO") && getenv("OB200_FUSED_HALO")[0] == '0' );
+    const bool fused_halo = allow_fused && p2p && comm->nneigh > 0 && comm->route.p && spmv_halo_supported(A);
+    const ob200_mailbox_layout ML = mailbox_layout(comm ? comm->nranks : 1, comm ? comm->cap : 1);
+    auto finish = [&](int stage, int iter, int nred, const double *pa = nullptr, int nA = 0, const double *pb = nullptr, int nB = 0) -> int {
         if ( !dist ) return OB200_OK;
+        if ( p2p ) {
+            const unsigned int seq = ++comm->scal_seq;
+            const int64_t par = seq & 1u;
+            OB_LAUNCH(ctx, cg_scalars_p2p_kernel, 1, kCgThreads, 0, stage, iter, tol, w.red, nred, w.S, comm->nranks, pa, nA, pb, nB,
+                      comm->p_sdata.p, reinterpret_cast< const unsigned long long * >( comm->mailbox + ML.sdata ),
+                      2 * par * ML.sdata_half, seq, reinterpret_cast< int * >( comm->mailbox + ML.error ));
+            return OB200_OK;
+        }
         OB_CHECK( comm_allreduce_sum(comm, w.red, nred) );
         OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, stage, iter, tol, w.red, w.S);
         return OB200_OK;
@@ -363,9 +437,27 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
                 int nb = 0;
                 OB_CHECK( spmv_fused_dot(A, w.p, w.q, w.partials, &nb, &w.S->done) );      // q = A p, partials of p.q
                 OB_LAUNCH(ctx, cg_pq_kernel< true >, 1, kCgThreads, 0, w.partials, nb, w.red, w.S);
+            } else if ( fused_halo ) {
+                // one kernel: q = A p, p.q over the rows only this rank holds, shared rows pushed to the sharers;
+                // the pull sums the sharers' values and adds p.q over the shared rows this rank owns
+                const unsigned int seq = ++comm->halo_seq;
+                static const bool fused_push = !( getenv("OB200_FUSED_PUSH") && getenv("OB200_FUSED_PUSH")[0] == '0' );
+                static const bool fake = getenv("OB200_DBG_FAKEROUTE") != nullptr;
+                static DevBuf< int32_t > fake_route;
+                if ( fake && !fake_route.p ) {
+                    OB_CHECK( fake_route.alloc(n) );
+                    OB_CUDA( cudaMemsetAsync(fake_route.p, 0xFF, sizeof( int32_t ) * (size_t) n, ctx->stream) );
+                }
+                const SpmvHalo hv{ fake ? fake_route.p : comm->route.p, comm->uniq_ptr.p, fused_push ? comm->push_dst.p : nullptr,
+                                   2 * (int64_t)( seq & 1u ) * ML.data_half, seq };
+                int nb = 0;
+                OB_CHECK( spmv_fused_halo(A, w.p, w.q, w.partials, &nb, &w.S->done, hv) );
+                if ( !fused_push ) OB_CHECK( comm_p2p_push(comm, w.q, seq, &w.S->done) );
+                OB_CHECK( comm_p2p_pull(comm, w.q, seq, w.p, &w.S->done) );
+                OB_CHECK( finish(1, it, 1, w.partials, nb, comm->pull_partials.p, comm->pull_grid) );
             } else {
                 OB_CHECK( spmv_fused_dot(A, w.p, w.q, nullptr, nullptr, &w.S->done) );
-                OB_CHECK( comm_exchange_add(comm, w.q) );
+                OB_CHECK( comm_exchange_add(comm, w.q, &w.S->done) );
                 OB_LAUNCH(ctx, cg_dot_kernel, G, kCgThreads, 0, n, w.p, w.q, owned, w.partials, w.red, w.S);
                 if ( dist ) OB_CHECK( finish(1, it, 1) );
                 else OB_LAUNCH(ctx, cg_scalars_kernel, 1, 1, 0, 1, it, tol, w.red, w.S);
@@ -378,6 +470,7 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
         OB_CUDA( cudaStreamSynchronize(ctx->stream) );
         done = h.done || it >= max_iter;
     }
+    if ( p2p ) OB_CHECK( comm_p2p_check(comm) );
     *iters = h.done ? h.iters : max_iter;
     *resid = h.resid;
     return h.done ? 0 : 1;        // cg.h: 0 converged, 1 max_iter reached

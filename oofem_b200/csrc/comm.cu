@@ -98,8 +98,9 @@ int comm_allreduce_sum(ob200_comm *c, double *dev, int n)
     return OB200_OK;
 }
 
-int comm_exchange_add(ob200_comm *c, double *y)
+int comm_exchange_add(ob200_comm *c, double *y, const int *done)
 {
+    if ( c->p2p ) return comm_p2p_exchange_add(c, y, done);
     if ( c->nshared == 0 ) return OB200_OK;
     ob200_context *ctx = c->ctx;
     int grid = ctx->shape.grid(c->nshared, 256, 4);
@@ -167,6 +168,9 @@ void ob200_comm_destroy(ob200_comm *c)
         cudaStreamSynchronize(c->ctx->stream);
         g_nccl.CommDestroy((ncclComm_t) c->nccl);
     }
+    for ( size_t r = 0; r < c->peer_base.size(); r++ )
+        if ( c->peer_base[r] && c->peer_base[r] != c->mailbox ) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if ( c->mailbox ) cudaFree(c->mailbox);
     delete c;
 }
 
@@ -225,6 +229,7 @@ int ob200_comm_set_halo(ob200_comm *c, int32_t neq, int nneigh, const int32_t *n
     if ( owned ) for ( int32_t i = 0; i < neq; i++ ) own[i] = owned[i] ? 1 : 0;
     OB_CHECK( put(c->owned, own.data(), neq) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    if ( c->p2p ) OB_CHECK( comm_p2p_prepare(c) );
     return OB200_OK;
 }
 

@@ -195,7 +195,8 @@ int ob200_csr_materialize(ob200_csr *A)
 
 namespace ob200 {
 
-static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done)
+static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done,
+                       const SpmvHalo *halo = nullptr)
 {
     ob200_context *ctx = A->ctx;
     if ( nblocks ) *nblocks = 0;
@@ -209,22 +210,29 @@ static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partial
         static bool attr_set = false;
         const int smem = (int) sizeof( SpmvShared );
         if ( !attr_set ) {
-            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< false >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
-            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
+            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< 0 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
+            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
+            OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< 2 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
             attr_set = true;
         }
         int grid = ctx->shape.sms * 2;                 // persistent: 2 CTAs per SM, 3 stages each in flight
         if ( grid > A->nchunks ) grid = A->nchunks;
-        if ( partials ) {
-            OB_LAUNCH(ctx, spmv_stream_kernel< true >, grid, kSpmvThreads, smem, A->neq, A->rowptr.p, A->colind.p, A->val.p,
-                      A->chunks.p, A->nchunks, x, y, partials, done);
+        const SpmvHalo none{ nullptr, nullptr, nullptr, 0, 0 };
+        if ( halo ) {
+            OB_LAUNCH(ctx, spmv_stream_kernel< 2 >, grid, kSpmvThreads, smem, A->neq, A->rowptr_flag.p, A->colind.p, A->val.p,
+                      A->chunks.p, A->nchunks, x, y, partials, done, *halo);
+            if ( nblocks ) *nblocks = grid;
+        } else if ( partials ) {
+            OB_LAUNCH(ctx, spmv_stream_kernel< 1 >, grid, kSpmvThreads, smem, A->neq, A->rowptr.p, A->colind.p, A->val.p,
+                      A->chunks.p, A->nchunks, x, y, partials, done, none);
             if ( nblocks ) *nblocks = grid;
         } else {
-            OB_LAUNCH(ctx, spmv_stream_kernel< false >, grid, kSpmvThreads, smem, A->neq, A->rowptr.p, A->colind.p, A->val.p,
-                      A->chunks.p, A->nchunks, x, y, partials, done);
+            OB_LAUNCH(ctx, spmv_stream_kernel< 0 >, grid, kSpmvThreads, smem, A->neq, A->rowptr.p, A->colind.p, A->val.p,
+                      A->chunks.p, A->nchunks, x, y, partials, done, none);
         }
         return OB200_OK;
     }
+    OB_REQUIRE(!halo, OB200_ECAPACITY, "spmv: rows longer than %d entries are not supported by the fused halo product", kSpmvSlack);
     // rows longer than the streamed kernel's stage: warp per row straight from global memory
     int grid = ctx->shape.grid((int64_t) A->neq * 32, 256, 8);
     if ( partials ) {
@@ -242,6 +250,27 @@ int spmv(ob200_csr *A, const double *x, double *y) { return spmv_launch(A, x, y,
 int spmv_fused_dot(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done)
 {
     return spmv_launch(A, x, y, partials, nblocks, done);
+}
+
+// distributed: q = A p, partial sums of p.q over the rows only this rank holds, shared rows pushed to the sharers
+bool spmv_halo_supported(const ob200_csr *A) { return A->maxrow <= kSpmvSlack && A->chunks.p && A->nnz > 0; }
+__global__ void flag_rowptr_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ route, int32_t *__restrict__ out)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i <= neq; i += stride )
+        out[i] = rowptr[i] | ( i < neq && route[i] >= 0 ? (int32_t) 0x80000000 : 0 );
+}
+
+int spmv_fused_halo(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done, const SpmvHalo &halo)
+{
+    ob200_context *ctx = A->ctx;
+    if ( A->flag_route != halo.route || A->rowptr_flag.n != (int64_t) A->neq + 1 + kCsrPad ) {
+        OB_CHECK( A->rowptr_flag.alloc((int64_t) A->neq + 1 + kCsrPad) );
+        OB_CUDA( cudaMemsetAsync(A->rowptr_flag.p, 0, sizeof( int32_t ) * (size_t)( A->neq + 1 + kCsrPad ), ctx->stream) );
+        OB_LAUNCH(ctx, flag_rowptr_kernel, ctx->shape.grid(A->neq + 1, 256, 8), 256, 0, A->neq, A->rowptr.p, halo.route, A->rowptr_flag.p);
+        A->flag_route = halo.route;
+    }
+    return spmv_launch(A, x, y, partials, nblocks, done, &halo);
 }
 } // namespace ob200
 
@@ -325,6 +354,7 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
     // CompCol stores colptr / rowind in IntArray (32-bit): keep the same limit and say so
     OB_REQUIRE(nnz < (int64_t) INT_MAX, OB200_ECAPACITY, "csr_build_structure: nnz=%lld exceeds the 32-bit range of the reference's IntArray", (long long) nnz);
     OB_CHECK( A->rowptr.alloc(neq + 1 + kCsrPad) );
+    A->flag_route = nullptr;
     OB_CHECK( narrow_i64_to_i32(ctx, rp64.p, A->rowptr.p, (int64_t) neq + 1) );
     OB_CHECK( A->colind.alloc(nnz + kCsrPad) );
     OB_CHECK( A->val.alloc(nnz + kCsrPad) );
@@ -482,3 +512,37 @@ int ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value)
 }
 
 } // extern "C"
+
+// scratch: time the three modes of the streamed SpMV on one GPU (route = -1 everywhere in mode 2)
+extern "C" int ob200_debug_spmv_modes(ob200_csr *A, const double *x_dev, double *y_dev, int reps, float *ms3)
+{
+    ob200::bind_stream(A->ctx);
+    ob200_context *ctx = A->ctx;
+    ob200::DevBuf< int32_t > route;
+    ob200::DevBuf< double > part;
+    OB_CHECK( route.alloc(A->neq) );
+    OB_CHECK( part.alloc(4096) );
+    OB_CUDA( cudaMemsetAsync(route.p, 0xFF, sizeof( int32_t ) * (size_t) A->neq, ctx->stream) );
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for ( int mode = 0; mode < 3; mode++ ) {
+        for ( int k = 0; k < reps + 2; k++ ) {
+            if ( k == 2 ) cudaEventRecord(e0, ctx->stream);
+            int nb = 0;
+            if ( mode == 0 ) OB_CHECK( ob200::spmv(A, x_dev, y_dev) );
+            if ( mode == 1 ) OB_CHECK( ob200::spmv_fused_dot(A, x_dev, y_dev, part.p, &nb, nullptr) );
+            if ( mode == 2 ) {
+                const ob200::SpmvHalo hv{ route.p, nullptr, nullptr, 0, 1 };
+                OB_CHECK( ob200::spmv_fused_halo(A, x_dev, y_dev, part.p, &nb, nullptr, hv) );
+            }
+        }
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(ms3 + mode, e0, e1);
+        ms3[mode] /= reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return OB200_OK;
+}

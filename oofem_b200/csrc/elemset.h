@@ -34,6 +34,10 @@ struct ob200_csr {
     // SparseMtrx::zero() is lazy: the memset is skipped when the next writer overwrites every entry
     // (the gather assembly does); any other reader/writer materialises it first (csr_materialize)
     bool zero_pending = false;
+    // distributed product (spmv.cuh MODE 2): copy of rowptr with the sign bit set on rows shared with other
+    // partitions, valid for the halo description `flag_route` it was built from
+    ob200::DevBuf< int32_t > rowptr_flag;
+    const int32_t *flag_route = nullptr;
     // CG work vectors (allocated on first solve)
     ob200::DevBuf< double > work;
     ob200::DevBuf< double > diag;

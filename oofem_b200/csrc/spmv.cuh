@@ -11,6 +11,8 @@
 #pragma once
 #include "common.cuh"
 
+#include "spmv_halo.h"
+
 namespace ob200 {
 
 constexpr int kSpmvConsumers = 256;                  // 8 consumer warps ...
@@ -94,20 +96,23 @@ __global__ void spmv_chunk_table_kernel(int32_t neq, const int32_t *__restrict__
     }
 }
 
-// y = A x.  FUSE_DOT: also partials[blockIdx.x] = sum over this CTA's rows of y[r]*x[r].
+// y = A x.  MODE 1: also partials[blockIdx.x] = sum over this CTA's rows of y[r]*x[r].
+// MODE 2 (distributed): the partial sums cover the rows only this rank holds, the local sums of shared
+// rows are pushed to the sharers' mailboxes (the halo exchange is fused into the epilogue).
 // `done` (may be null): device flag, the kernel is a no-op once it is set (CG early exit).
 //
 // Warp-specialised: warp 8 (one lane) is the producer -- it walks this CTA's chunks, waits for a
 // free stage, and issues three bulk copies (values, column indices, row pointers) that complete on
 // the stage's "full" mbarrier; warps 0-7 consume: products in place, then row sums, then release
 // the stage through its "empty" mbarrier.
-template< bool FUSE_DOT >
+template< int MODE >
 __global__ void __launch_bounds__(kSpmvThreads, 2)
 spmv_stream_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
                    const double *__restrict__ val, const int2 *__restrict__ table, int32_t nchunks,
                    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partials,
-                   const int *__restrict__ done)
+                   const int *__restrict__ done, SpmvHalo halo)
 {
+    constexpr bool FUSE_DOT = MODE != 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmvShared &sh = *reinterpret_cast< SpmvShared * >( smem_raw );
     if ( done && *done ) return;
@@ -183,15 +188,27 @@ spmv_stream_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_
         for ( int rb = m.row0; rb < m.row1; rb += kRowsPerPass ) {
             const int r = rb + gw * kWarps + wid;
             double s0 = 0.0, s1 = 0.0;
+            // what the epilogue needs, requested before the row is summed
+            double xr = 0.0;
+            bool shared_row = false;
+            if ( MODE != 0 && r < m.row1 ) xr = __ldg(x + r);
             if ( r < m.row1 ) {
                 int b, e;
                 if ( rows_staged ) {
-                    b = st.rp[r - ra0] - a0;
-                    e = st.rp[r + 1 - ra0] - a0;
+                    b = st.rp[r - ra0];
+                    e = st.rp[r + 1 - ra0];
                 } else {
-                    b = rowptr[r] - a0;
-                    e = rowptr[r + 1] - a0;
+                    b = rowptr[r];
+                    e = rowptr[r + 1];
                 }
+                if ( MODE == 2 ) {
+                    // the distributed product runs on a copy of the row pointers whose sign bit marks the shared rows
+                    shared_row = b < 0;
+                    b &= 0x7fffffff;
+                    e &= 0x7fffffff;
+                }
+                b -= a0;
+                e -= a0;
                 int i = b + gl;
                 for ( ; i + 3 * kSpmvLanesPerRow < e; i += 4 * kSpmvLanesPerRow ) {
                     const int c0 = st.col[i], c1 = st.col[i + 8], c2 = st.col[i + 16], c3 = st.col[i + 24];
@@ -209,7 +226,15 @@ spmv_stream_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_
             for ( int o = kSpmvLanesPerRow / 2; o > 0; o >>= 1 ) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
             if ( r < m.row1 && gl == 0 ) {
                 y[r] = s0;
-                if ( FUSE_DOT ) pq += s0 * __ldg(x + r);
+                if ( MODE == 1 ) pq += s0 * xr;
+                if ( MODE == 2 ) {
+                    if ( !shared_row ) pq += s0 * xr;
+                    else if ( halo.dst ) {
+                        const int u = __ldg(halo.route + r);
+                        for ( int i = __ldg(halo.uptr + u), e2 = __ldg(halo.uptr + u + 1); i < e2; i++ )
+                            ll_store(halo.dst[i] + halo.half_words, s0, halo.seq);
+                    }
+                }
             }
         }
         __syncwarp();

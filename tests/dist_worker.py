@@ -74,7 +74,8 @@ def main():
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     ok = e_spmv < 1e-12 and e_u < 1e-8 and flag == 0 and int(lo) == int(hi)
     print(json.dumps({"rank": rank, "ok": bool(ok), "spmv_relerr": e_spmv, "u_relerr": e_u, "flag": flag,
-                      "iters": solver.last_iterations}), flush=True)
+                      "iters": solver.last_iterations, "p2p": comm.p2p}), flush=True)
+    dist.barrier()           # nobody unmaps a mailbox a peer may still write
     comm.close()
     ctx.close()
     dist.barrier()
