@@ -94,6 +94,7 @@ class StaticStructural:
         self.nsmax = pb.params.get("maxiter", 100)
         self.solution = np.zeros(d.neq)
         self.iterations = []
+        self.trace = []                 # (step, iteration, force error, CG iterations of the previous solve)
         self.tangent_assemblies = 0
 
     def updateMatrix(self):
@@ -139,6 +140,7 @@ class StaticStructural:
             fint = self.internal_forces(t)
             rhs = fext - fint
             err = self.force_error(rhs, fext)
+            self.trace.append((step, nite, err, self.linSolver.last_iterations))
             if err <= self.rtolf and ( nite > 0 or err == 0.0 ):
                 break
             if nite >= self.nsmax:

@@ -63,6 +63,22 @@ if os.path.exists(rep):
                 if k in hdr:
                     i = hdr.index(k)
                     f.write(f"    {k:82s} {r[i]} {units[i]}\n")
+    # DRAM bytes per launch of the two dominant kernels -> profiles/traffic.json (bench.py roofline.traffic)
+    import json
+    traffic = {"source": f"ncu --set full ({tag}), dram__bytes_read.sum + dram__bytes_write.sum per launch at the 1M-hex config"}
+    conv = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ir, iw, ik = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('Kernel Name')
+    best = {}
+    for r in rows[2:]:
+        for key in ("spmv_stream_kernel", "lspace_gather_kernel"):
+            if key in r[ik]:
+                b = float(r[ir].replace(',', '')) * conv.get(units[ir], 1.0) + float(r[iw].replace(',', '')) * conv.get(units[iw], 1.0)
+                best.setdefault(key, []).append(b)
+    for key, v in best.items():
+        v.sort()
+        traffic[key] = v[len(v) // 2]          # median launch
+    if len(traffic) > 1:
+        json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 for fn in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
     if os.path.exists(os.path.join(G, fn)):
         shutil.copy(os.path.join(G, fn), os.path.join(P, fn))
