@@ -203,6 +203,7 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
     const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
     const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
     constexpr int Q = kMaxValence * 8 / 32;          // items per lane
+    __shared__ int sm_key[8][Q * 32], sm_dkey[8][Q * 32], sm_dinfo[8][Q * 32], sm_dblk[8][Q * 32];
     for ( int64_t w = warp0; w < nnode; w += nwarps ) {
         const int v0 = ninc_start[w], nv = ninc_start[w + 1] - v0;
         const int nitems = nv * 8;
@@ -230,61 +231,70 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
                 if ( !ok ) atomicAdd(flags, 1);
             }
         }
-        const int nq = ( nitems + 31 ) >> 5;
-        // value of per-item register array `arr` of item jt = q2*32 + src, broadcast to the warp
-#define ITEM_BCAST(arr, dflt)                                        \
-    ( [&]() {                                                        \
-        int sel__ = dflt;                                            \
-        _Pragma("unroll") for ( int qs = 0; qs < Q; qs++ ) if ( qs == q2 ) sel__ = arr[qs]; \
-        return __shfl_sync(0xffffffffu, sel__, src);                 \
-    }() )
+        // the per-item data the passes below broadcast go through this warp's slice of shared memory
+        int *skey = sm_key[threadIdx.x >> 5], *dkey = sm_dkey[threadIdx.x >> 5], *dinfo = sm_dinfo[threadIdx.x >> 5],
+            *dblk = sm_dblk[threadIdx.x >> 5];
+        __syncwarp();
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) skey[q * 32 + lane] = key[q];
+        __syncwarp();
         // pass 1: rank inside my key (same key, earlier item) and size of my key
         int same_before[Q], same_total[Q];
 #pragma unroll
         for ( int q = 0; q < Q; q++ ) same_before[q] = same_total[q] = 0;
-        for ( int q2 = 0; q2 < nq; q2++ )
-            for ( int src = 0; src < 32 && q2 * 32 + src < nitems; src++ ) {
-                const int jt = q2 * 32 + src;
-                const int kj = ITEM_BCAST(key, INT_MAX);
+        for ( int jt = 0; jt < nitems; jt++ ) {
+            const int kj = skey[jt];
 #pragma unroll
-                for ( int q = 0; q < Q; q++ ) {
-                    same_total[q] += ( kj == key[q] );
-                    same_before[q] += ( kj == key[q] && jt < q * 32 + lane );
-                }
+            for ( int q = 0; q < Q; q++ ) {
+                same_total[q] += ( kj == key[q] );
+                same_before[q] += ( kj == key[q] && jt < q * 32 + lane );
             }
-        int first[Q];
+        }
+        // the distinct keys (= column blocks), compacted in item order
+        int first[Q], width[Q], ndist = 0;
 #pragma unroll
-        for ( int q = 0; q < Q; q++ ) first[q] = ( same_before[q] == 0 && cm[q] != 0 ) ? 1 : 0;
+        for ( int q = 0; q < Q; q++ ) {
+            first[q] = ( same_before[q] == 0 && cm[q] != 0 ) ? 1 : 0;
+            width[q] = __popc(cm[q]);
+            const unsigned int m = __ballot_sync(0xffffffffu, first[q]);
+            if ( first[q] ) {
+                const int c = ndist + __popc(m & ( ( 1u << lane ) - 1u ));
+                dkey[c] = key[q];
+                dinfo[c] = width[q] | ( same_total[q] << 8 );
+                first[q] = c + 1;                    // remember where this block sits in the compact list
+            }
+            ndist += __popc(m);
+        }
+        __syncwarp();
         // pass 2: distinct smaller keys (= my column block) and their total width (= my first column)
-        int blkidx[Q], cstart[Q], width[Q];
+        int blkidx[Q], cstart[Q];
 #pragma unroll
-        for ( int q = 0; q < Q; q++ ) { blkidx[q] = cstart[q] = 0; width[q] = __popc(cm[q]); }
-        for ( int q2 = 0; q2 < nq; q2++ )
-            for ( int src = 0; src < 32 && q2 * 32 + src < nitems; src++ ) {
-                const int kj = ITEM_BCAST(key, INT_MAX), fj = ITEM_BCAST(first, 0), wj = ITEM_BCAST(width, 0);
+        for ( int q = 0; q < Q; q++ ) blkidx[q] = cstart[q] = 0;
+        for ( int jd = 0; jd < ndist; jd++ ) {
+            const int kj = dkey[jd], wj = dinfo[jd] & 0xFF;
 #pragma unroll
-                for ( int q = 0; q < Q; q++ )
-                    if ( fj && kj < key[q] ) { blkidx[q]++; cstart[q] += wj; }
-            }
+            for ( int q = 0; q < Q; q++ )
+                if ( kj < key[q] ) { blkidx[q]++; cstart[q] += wj; }
+        }
+#pragma unroll
+        for ( int q = 0; q < Q; q++ )
+            if ( first[q] ) dblk[first[q] - 1] = blkidx[q];
+        __syncwarp();
         // pass 3: parking position.  Blocks are handled 32 at a time (one per lane) by the assembly
         // kernel, which walks "the i-th item of every block that has one" for i = 0, 1, ...; items are
         // parked in exactly that order (jagged-diagonal order) so that each step reads contiguous slots.
         int park[Q];
 #pragma unroll
         for ( int q = 0; q < Q; q++ ) park[q] = 0;
-        for ( int q2 = 0; q2 < nq; q2++ )
-            for ( int src = 0; src < 32 && q2 * 32 + src < nitems; src++ ) {
-                const int fj = ITEM_BCAST(first, 0);
-                if ( !fj ) continue;
-                const int bj = ITEM_BCAST(blkidx, 0), cj = ITEM_BCAST(same_total, 0);
+        for ( int jd = 0; jd < ndist; jd++ ) {
+            const int bj = dblk[jd], cj = dinfo[jd] >> 8;
 #pragma unroll
-                for ( int q = 0; q < Q; q++ ) {
-                    const int i = same_before[q];
-                    if ( ( bj >> 5 ) < ( blkidx[q] >> 5 ) ) park[q] += cj;
-                    else if ( ( bj >> 5 ) == ( blkidx[q] >> 5 ) ) park[q] += min(cj, i) + ( ( bj < blkidx[q] && cj > i ) ? 1 : 0 );
-                }
+            for ( int q = 0; q < Q; q++ ) {
+                const int i = same_before[q];
+                if ( ( bj >> 5 ) < ( blkidx[q] >> 5 ) ) park[q] += cj;
+                else if ( ( bj >> 5 ) == ( blkidx[q] >> 5 ) ) park[q] += min(cj, i) + ( ( bj < blkidx[q] && cj > i ) ? 1 : 0 );
             }
-#undef ITEM_BCAST
+        }
         // the node's own rows (any free dof; all of them share the pattern)
         const int r0 = nodeeq[w * 3], r1 = nodeeq[w * 3 + 1], r2 = nodeeq[w * 3 + 2];
         const int row = r0 > 0 ? r0 - 1 : ( r1 > 0 ? r1 - 1 : ( r2 > 0 ? r2 - 1 : -1 ) );

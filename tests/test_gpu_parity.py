@@ -150,6 +150,48 @@ def test_full_path_vs_oracle(ctx, etype, dims):
     assert relerr(ug, sol["u"]) < TOL_U
 
 
+def test_gather_assembly_irregular_numbering_vs_oracle(ctx):
+    """The owner-computes assembly on a mesh whose node and element numbers are random: a group of
+    consecutive nodes then touches unrelated elements (more distinct elements than one geometry round
+    holds, element lists of a node in arbitrary order), two materials, and a second assembly that
+    accumulates on top of the first (SparseMtrx::assemble adds)."""
+    pb = _random_problem("lspace", 9, 5, 4, seed=11, mat=Material("isole", 210e3, 0.3))
+    rng = np.random.default_rng(7)
+    nnode, nelem = pb.coords.shape[0], pb.conn.shape[0]
+    perm = rng.permutation(nnode)                      # old node i -> new node perm[i]
+    coords = np.empty_like(pb.coords)
+    coords[perm] = pb.coords
+    conn = (perm[pb.conn - 1] + 1).astype(np.int32)[rng.permutation(nelem)]
+    pb.coords, pb.conn = coords, np.ascontiguousarray(conn)
+    for bc in pb.bcs:
+        bc.nodes = perm[bc.nodes - 1] + 1
+    for ld in pb.loads:
+        ld.nodes = perm[ld.nodes - 1] + 1
+    pb.materials = [Material("isole", 210e3, 0.3), Material("isole", 70e3, 0.2)]
+    pb.elem_mat = rng.integers(0, 2, size=nelem).astype(np.int32)
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    rp, ci = A.structure()
+    assert np.array_equal(rp, md.colptr) and np.array_equal(ci, md.rowind)
+    Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams)
+    val_o = orc.compcol_assemble(md.loc, Ke_o, md.colptr, md.rowind)
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    A.zero()
+    dom.elems.assembleStiffness(A)
+    assert relerr(A.values(), val_o) < TOL_KE
+    dom.elems.assembleStiffness(A)                     # no zero() in between: contributions add up
+    assert relerr(A.values(), 2.0 * val_o) < TOL_KE
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    assert prof.get("lspace_gather_kernel< false >", (0, 0))[1] == 1 and prof.get("lspace_gather_kernel< true >", (0, 0))[1] == 1, prof
+    sol = orc.solve_linear_static(pb)
+    ug = LinearStatic(ctx, pb).solveYourselfAt(1.0)
+    assert relerr(ug, sol["u"]) < TOL_U
+
+
 @pytest.mark.parametrize("etype", ["lspace", "ltrspace"])
 def test_mises_material_point_vs_oracle(ctx, etype):
     """Stress return, state update, algorithmic tangent and commit on random strains."""
