@@ -358,8 +358,11 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ---------------------------------------------
     peak, peak_src = load_peaks()
     # the CG product: fused p.q on one GPU (< 1 >), fused p.q + halo push over peer memory (< 2 >), plain (< 0 >, NCCL)
-    spmv_name = max(("spmv_stream_kernel< 1 >", "spmv_stream_kernel< 2 >", "spmv_stream_kernel< 0 >"),
+    spmv_name = max(("spmv_block_kernel< MODE >", "spmv_stream_kernel< 1 >", "spmv_stream_kernel< 2 >", "spmv_stream_kernel< 0 >"),
                     key=lambda k: prof.get(k, (0.0, 0))[0])
+    layout = (C.c_int64 * 3)()
+    check(lib().ob200_csr_spmv_layout(A.h, layout))
+    blocked, nrb, nblk = int(layout[0]), int(layout[1]), int(layout[2])
     asm_name = next((k for k in ("lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
                                  "lspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_gather_kernel< false >")
     ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
@@ -367,6 +370,10 @@ def run_ours(args):
     # algorithmic bytes: SpMV reads val (8 B) + colind (4 B) per non-zero, and per
     # row rowptr (4 B), the operand entry once (8 B), writes the result (8 B)
     spmv_bytes = 12.0 * nnz + 20.0 * neq
+    if blocked:
+        # blocked index: 8 B of value per non-zero, 8 B per column block, 16 B per row block,
+        # x once and y once per row
+        spmv_bytes = 8.0 * nnz + 8.0 * nblk + 16.0 * nrb + 16.0 * neq
     spmv_dur = ms_spmv / max(n_spmv, 1) * 1e-3
     spmv_gbs = spmv_bytes / spmv_dur / 1e9 if spmv_dur > 0 else 0.0
     # assembly: per element conn (32 B) + matid (4 B) + location array (96 B), coordinates once per node
@@ -379,7 +386,7 @@ def run_ours(args):
     except Exception:
         traffic = {}
     full_size = (nx, ny, nz) == (250, 64, 64)         # the captures were taken at this size
-    spmv_traffic = traffic.get("spmv_stream_kernel") if full_size else None
+    spmv_traffic = traffic.get(spmv_name.split("<")[0].strip()) if full_size else None
     asm_traffic = traffic.get("lspace_gather_kernel") if full_size and asm_name.startswith("lspace_gather") else None
     kernel_share = {k: round(v[0] / (t_step * args.steps) , 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
 
@@ -406,7 +413,11 @@ def run_ours(args):
                    "structure_build_s": round(t_structure, 4)},
         "roofline": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                      "frac": spmv_gbs / peak, "traffic": spmv_traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_dur * 1e3, "launches": n_spmv},
+                     "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_dur * 1e3, "launches": n_spmv,
+                     "index": ("blocked: %d row blocks, %d column blocks for %d non-zeros; plain CSR would read %.3f GB "
+                               "(%.0f GB/s at this duration)" % (nrb, nblk, nnz, (12.0 * nnz + 20.0 * neq) / 1e9,
+                                                                 (12.0 * nnz + 20.0 * neq) / spmv_dur / 1e9 if spmv_dur > 0 else 0.0))
+                              if blocked else "CSR"},
         "roofline_assembly": {"kernel": asm_name, "bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s",
                               "frac": asm_gbs / peak, "traffic": asm_traffic, "algorithmic_bytes_per_launch": asm_bytes,
                               "avg_launch_ms": asm_dur * 1e3, "launches": n_asmk,

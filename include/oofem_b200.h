@@ -85,7 +85,11 @@ void ob200_csr_destroy(ob200_csr *A);
  * loc x loc (non-zero entries), rows sorted ascending.  loc is [nelem][ndofel]. */
 int  ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t ndofel,
                                const int32_t *loc, int on_device);
-int32_t ob200_csr_rows(const ob200_csr *A);                 /* SparseMtrx::giveNumberOfRows */
+int32_t ob200_csr_rows(const ob200_csr *A);
+/* How SparseMtrx::times reads the matrix: info[0] = 1 if the blocked index is in use (rows of a node share
+ * one pattern, columns of a node are consecutive: oofem_b200/csrc/spmv_block.cuh), info[1] = row blocks,
+ * info[2] = column blocks; all 0 for plain CSR.  rowptr/colind are the same in both cases. */
+int  ob200_csr_spmv_layout(ob200_csr *A, int64_t *info3);                 /* SparseMtrx::giveNumberOfRows */
 int64_t ob200_csr_nnz(const ob200_csr *A);
 /* copy out rowptr[neq+1], colind[nnz] (0-based, like CompCol's colptr/rowind) and val[nnz] */
 int  ob200_csr_get_structure(const ob200_csr *A, int32_t *rowptr, int32_t *colind, int on_device);

@@ -69,6 +69,7 @@ SYMBOLS = {
     "ob200_elemset_get_state": (_int, [_vp, _vp, _int]),
     "ob200_elemset_set_state": (_int, [_vp, _vp, _int]),
     "ob200_cg_solve": (_int, [_vp, _vp, _vp, _int, _int, _dbl, C.POINTER(_int), C.POINTER(_dbl), _int]),
+    "ob200_csr_spmv_layout": (_int, [_vp, _vp]),
     "ob200_comm_unique_id": (_int, [_vp]),
     "ob200_comm_create": (_int, [_vp, _int, _int, _vp, _pp]),
     "ob200_comm_destroy": (None, [_vp]),

@@ -9,6 +9,9 @@
 #include "elemset.h"
 #include "scan.cuh"
 #include "spmv.cuh"
+#include "spmv_block.cuh"
+#include <stdlib.h>
+#include <vector>
 #include <limits.h>
 
 namespace ob200 {
@@ -195,6 +198,88 @@ int ob200_csr_materialize(ob200_csr *A)
 
 namespace ob200 {
 
+// Derive the blocked index (spmv_block.cuh) from rowptr/colind; leaves blk_ok = false when the matrix has no
+// node-block structure worth using or a chunk would not fit the stage.
+static int csr_build_blocks(ob200_csr *A)
+{
+    ob200_context *ctx = A->ctx;
+    A->blk_tried = true;
+    A->blk_ok = false;
+    if ( getenv("OB200_SPMV_BLOCKED") && getenv("OB200_SPMV_BLOCKED")[0] == '0' ) return OB200_OK;
+    const int32_t neq = A->neq;
+    if ( neq == 0 || A->nnz == 0 || A->maxrow > kSpmvSlack ) return OB200_OK;
+    // rows that repeat the pattern of the row before them -> row blocks of up to 3 rows (host pass over neq flags)
+    DevBuf< unsigned char > same;
+    OB_CHECK( same.alloc(neq) );
+    OB_LAUNCH(ctx, blk_row_same_kernel, ctx->shape.grid((int64_t) neq * 32, 256, 8), 256, 0, neq, A->rowptr.p, A->colind.p, same.p);
+    std::vector< unsigned char > hs(neq);
+    OB_CUDA( cudaMemcpyAsync(hs.data(), same.p, (size_t) neq, cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    std::vector< int32_t > rbrow;
+    rbrow.reserve(neq / 2 + 2);
+    int run = 0;
+    for ( int32_t r = 0; r < neq; r++ ) {
+        if ( r > 0 && hs[r] && run < 3 ) run++;
+        else { rbrow.push_back(r); run = 1; }
+    }
+    const int32_t nrb = (int32_t) rbrow.size();
+    rbrow.push_back(neq);
+    DevBuf< int32_t > d_rbrow, cnt;
+    DevBuf< int64_t > b0;
+    OB_CHECK( d_rbrow.alloc(nrb + 1) );
+    OB_CHECK( cnt.alloc(nrb + 1) );
+    OB_CHECK( b0.alloc(nrb + 1) );
+    OB_CUDA( cudaMemcpyAsync(d_rbrow.p, rbrow.data(), sizeof( int32_t ) * (size_t)( nrb + 1 ), cudaMemcpyHostToDevice, ctx->stream) );
+    OB_CUDA( cudaMemsetAsync(cnt.p, 0, sizeof( int32_t ) * (size_t)( nrb + 1 ), ctx->stream) );
+    const int grid = ctx->shape.grid((int64_t) nrb * 32, 256, 8);
+    OB_LAUNCH(ctx, blk_columns_kernel< false >, grid, 256, 0, nrb, d_rbrow.p, A->rowptr.p, A->colind.p, cnt.p, nullptr, nullptr, nullptr);
+    int64_t nblk = 0;
+    OB_CHECK( exclusive_scan(ctx, cnt.p, b0.p, nrb + 1, &nblk) );
+    // worth it?  index bytes per non-zero must drop well below the 4 B of colind
+    if ( nblk * kBlkMinRatio > A->nnz || nblk >= ( (int64_t) 1 << 31 ) ) return OB200_OK;
+    OB_CHECK( A->bw.alloc(nblk + 8) );
+    OB_CHECK( A->rbdesc.alloc(nrb + 1) );
+    OB_CUDA( cudaMemsetAsync(A->bw.p + nblk, 0, sizeof( uint2 ) * 8, ctx->stream) );
+    OB_LAUNCH(ctx, blk_columns_kernel< true >, grid, 256, 0, nrb, d_rbrow.p, A->rowptr.p, A->colind.p, cnt.p, b0.p, A->bw.p, A->rbdesc.p);
+    const int4 sentinel = make_int4(neq, (int) A->nnz, (int) nblk, 0);
+    OB_CUDA( cudaMemcpyAsync(A->rbdesc.p + nrb, &sentinel, sizeof( int4 ), cudaMemcpyHostToDevice, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    const int32_t nchunks = (int32_t)( ( A->nnz - 1 ) / kBlkChunk + 1 );
+    OB_CHECK( A->bchunks.alloc(nchunks + 1) );
+    OB_LAUNCH(ctx, blk_chunk_table_kernel, ctx->shape.grid((int64_t) nrb + 1, 256, 8), 256, 0, nrb, A->rbdesc.p, nchunks, A->bchunks.p);
+    std::vector< int4 > ht(nchunks + 1);
+    OB_CUDA( cudaMemcpyAsync(ht.data(), A->bchunks.p, sizeof( int4 ) * (size_t)( nchunks + 1 ), cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    for ( int32_t c = 0; c < nchunks; c++ ) {
+        const int4 t0 = ht[c], t1 = ht[c + 1];
+        if ( t1.y - ( t0.y & ~1 ) + 1 > kBlkValCap - 8 || t1.z - ( t0.z & ~1 ) + 1 > kBlkCap || t1.x - t0.x > kRbCap ) return OB200_OK;
+    }
+    A->nrb = nrb;
+    A->nblk = nblk;
+    A->nbchunks = nchunks;
+    A->blk_ok = true;
+    return OB200_OK;
+}
+
+template< int MODE >
+static int spmv_block_launch(ob200_csr *A, const int4 *desc, const double *x, double *y, double *partials, int *nblocks,
+                             const int *done, const SpmvHalo &hv)
+{
+    ob200_context *ctx = A->ctx;
+    static bool attr_set = false;
+    const int smem = (int) sizeof( SpmvBlkShared );
+    if ( !attr_set ) {
+        OB_CUDA( cudaFuncSetAttribute(spmv_block_kernel< MODE >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
+        attr_set = true;
+    }
+    int grid = ctx->shape.sms * kBlkCtas;
+    if ( grid > A->nbchunks ) grid = A->nbchunks;
+    OB_LAUNCH(ctx, spmv_block_kernel< MODE >, grid, kSpmvThreads, smem, A->val.p, A->bw.p, desc, A->bchunks.p, A->nbchunks, x, y,
+              partials, done, hv);
+    if ( nblocks && MODE != 0 ) *nblocks = grid;
+    return OB200_OK;
+}
+
 static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done,
                        const SpmvHalo *halo = nullptr)
 {
@@ -205,6 +290,13 @@ static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partial
     if ( A->nnz == 0 ) {
         OB_CUDA( cudaMemsetAsync(y, 0, sizeof( double ) * (size_t) A->neq, ctx->stream) );
         return OB200_OK;
+    }
+    if ( !A->blk_tried ) OB_CHECK( csr_build_blocks(A) );
+    if ( A->blk_ok ) {
+        const SpmvHalo none{ nullptr, nullptr, nullptr, 0, 0 };
+        if ( halo ) return spmv_block_launch< 2 >(A, A->rbdesc_flag.p, x, y, partials, nblocks, done, *halo);
+        if ( partials ) return spmv_block_launch< 1 >(A, A->rbdesc.p, x, y, partials, nblocks, done, none);
+        return spmv_block_launch< 0 >(A, A->rbdesc.p, x, y, partials, nblocks, done, none);
     }
     if ( A->maxrow <= kSpmvSlack && A->chunks.p ) {
         static bool attr_set = false;
@@ -264,6 +356,15 @@ __global__ void flag_rowptr_kernel(int32_t neq, const int32_t *__restrict__ rowp
 int spmv_fused_halo(ob200_csr *A, const double *x, double *y, double *partials, int *nblocks, const int *done, const SpmvHalo &halo)
 {
     ob200_context *ctx = A->ctx;
+    if ( !A->blk_tried ) OB_CHECK( csr_build_blocks(A) );
+    if ( A->blk_ok ) {
+        if ( A->flag_route != halo.route || A->rbdesc_flag.n != (int64_t) A->nrb + 1 ) {
+            OB_CHECK( A->rbdesc_flag.alloc((int64_t) A->nrb + 1) );
+            OB_LAUNCH(ctx, blk_flag_desc_kernel, ctx->shape.grid((int64_t) A->nrb + 1, 256, 8), 256, 0, A->nrb, A->rbdesc.p, halo.route, A->rbdesc_flag.p);
+            A->flag_route = halo.route;
+        }
+        return spmv_launch(A, x, y, partials, nblocks, done, &halo);
+    }
     if ( A->flag_route != halo.route || A->rowptr_flag.n != (int64_t) A->neq + 1 + kCsrPad ) {
         OB_CHECK( A->rowptr_flag.alloc((int64_t) A->neq + 1 + kCsrPad) );
         OB_CUDA( cudaMemsetAsync(A->rowptr_flag.p, 0, sizeof( int32_t ) * (size_t)( A->neq + 1 + kCsrPad ), ctx->stream) );
@@ -289,6 +390,16 @@ int ob200_csr_create(ob200_context *ctx, ob200_csr **out)
 void ob200_csr_destroy(ob200_csr *A) { delete A; }
 
 int32_t ob200_csr_rows(const ob200_csr *A) { return A ? A->neq : 0; }
+int ob200_csr_spmv_layout(ob200_csr *A, int64_t *info)
+{
+    OB_REQUIRE(A && info, OB200_EINVAL, "csr_spmv_layout: null argument");
+    ob200::bind_stream(A->ctx);
+    if ( !A->blk_tried && A->rowptr.p ) OB_CHECK( ob200::csr_build_blocks(A) );
+    info[0] = A->blk_ok ? 1 : 0;
+    info[1] = A->blk_ok ? A->nrb : 0;
+    info[2] = A->blk_ok ? A->nblk : 0;
+    return OB200_OK;
+}
 int64_t ob200_csr_nnz(const ob200_csr *A) { return A ? A->nnz : 0; }
 int64_t ob200_csr_version(const ob200_csr *A) { return A ? A->version : 0; }
 
@@ -355,6 +466,7 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
     OB_REQUIRE(nnz < (int64_t) INT_MAX, OB200_ECAPACITY, "csr_build_structure: nnz=%lld exceeds the 32-bit range of the reference's IntArray", (long long) nnz);
     OB_CHECK( A->rowptr.alloc(neq + 1 + kCsrPad) );
     A->flag_route = nullptr;
+    A->blk_tried = A->blk_ok = false;
     OB_CHECK( narrow_i64_to_i32(ctx, rp64.p, A->rowptr.p, (int64_t) neq + 1) );
     OB_CHECK( A->colind.alloc(nnz + kCsrPad) );
     OB_CHECK( A->val.alloc(nnz + kCsrPad) );

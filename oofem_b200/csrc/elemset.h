@@ -34,6 +34,12 @@ struct ob200_csr {
     // SparseMtrx::zero() is lazy: the memset is skipped when the next writer overwrites every entry
     // (the gather assembly does); any other reader/writer materialises it first (csr_materialize)
     bool zero_pending = false;
+    // blocked index of the SpMV (spmv_block.cuh), derived from rowptr/colind on first use
+    bool blk_tried = false, blk_ok = false;
+    int32_t nrb = 0, nbchunks = 0;
+    int64_t nblk = 0;
+    ob200::DevBuf< uint2 > bw;
+    ob200::DevBuf< int4 > rbdesc, rbdesc_flag, bchunks;
     // distributed product (spmv.cuh MODE 2): copy of rowptr with the sign bit set on rows shared with other
     // partitions, valid for the halo description `flag_route` it was built from
     ob200::DevBuf< int32_t > rowptr_flag;

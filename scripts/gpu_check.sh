@@ -17,6 +17,6 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --cg-iters 20 --no-cpu-baseline --no-e2e > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 echo "== ncu full"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'spmv_stream_kernel|lspace_gather_kernel|lspace_stiffness_kernel|cg_update_xr_kernel' -c 9 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'spmv_block_kernel|spmv_stream_kernel|lspace_gather_kernel|lspace_stiffness_kernel|cg_update_xr_kernel' -c 9 \
     -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --cg-iters 4 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT

@@ -70,7 +70,7 @@ if os.path.exists(rep):
     ir, iw, ik = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('Kernel Name')
     best = {}
     for r in rows[2:]:
-        for key in ("spmv_stream_kernel", "lspace_gather_kernel"):
+        for key in ("spmv_block_kernel", "spmv_stream_kernel", "lspace_gather_kernel"):
             if key in r[ik]:
                 b = float(r[ir].replace(',', '')) * conv.get(units[ir], 1.0) + float(r[iw].replace(',', '')) * conv.get(units[iw], 1.0)
                 best.setdefault(key, []).append(b)
