@@ -12,6 +12,7 @@
 #include "elemset.h"
 #include "comm.h"
 #include "spmv_halo.h"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 namespace ob200 {
@@ -259,6 +260,75 @@ cg_update_xr_kernel(int32_t neq, double *__restrict__ x, double *__restrict__ r,
     }
 }
 
+// One-GPU iteration tail in ONE cooperative launch (cg.h:54-66 and 45-52 of the next iteration):
+//   alpha = rho / p.q (every CTA sums the SpMV's per-CTA partials in the same fixed order),
+//   x += alpha p, r -= alpha q, partial sums of r.r and r.z,
+//   grid barrier, every CTA sums the partials in the same fixed order -> resid, rho, beta,
+//   p = z + beta p for the next iteration (r and p of this CTA's range are still in L2).
+// Replaces cg_pq_kernel + cg_update_xr_kernel + cg_update_p_kernel: two launches per iteration instead
+// of four, and the second pass over r/p no longer goes to HBM.
+__global__ void __launch_bounds__(kCgThreads)
+cg_xr_p_kernel(int32_t neq, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p, const double *__restrict__ q,
+               const double *__restrict__ diag, const double *__restrict__ spmv_partials, int nb, double *__restrict__ partials,
+               int P, double *__restrict__ red, int iter, double tol, CgScalars *S)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double scratch[32];
+    __shared__ double bc[2];
+    if ( S->done ) return;               // uniform: S is only written behind the grid barrier
+    const double rho = S->rho, normb = S->normb;
+    double pq = sum_partials(spmv_partials, nb, scratch);
+    if ( threadIdx.x == 0 ) bc[0] = pq;
+    __syncthreads();
+    const double alpha = rho / bc[0];                    // alpha = rho / dot(p, q)     (cg.h:54)
+    double rr = 0.0, rz = 0.0;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    // two (three) independent elements per trip: ten (fifteen) loads in flight per thread
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for ( ; i + 2 * stride < neq; i += 3 * stride ) {
+        const int64_t j = i + stride, k = j + stride;
+        const double pi = p[i], pj = p[j], pk = p[k], qi = q[i], qj = q[j], qk = q[k];
+        const double xi = x[i], xj = x[j], xk = x[k], r0i = r[i], r0j = r[j], r0k = r[k];
+        const double di = diag ? diag[i] : 1.0, dj = diag ? diag[j] : 1.0, dk = diag ? diag[k] : 1.0;
+        const double ri = r0i - alpha * qi, rj = r0j - alpha * qj, rk = r0k - alpha * qk;
+        x[i] = xi + alpha * pi; x[j] = xj + alpha * pj; x[k] = xk + alpha * pk;
+        r[i] = ri; r[j] = rj; r[k] = rk;
+        rr += ri * ri; rz += ri * ( diag ? ri * di : ri );
+        rr += rj * rj; rz += rj * ( diag ? rj * dj : rj );
+        rr += rk * rk; rz += rk * ( diag ? rk * dk : rk );
+    }
+    for ( ; i < neq; i += stride ) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        rr += ri * ri;
+        rz += ri * ( diag ? ri * diag[i] : ri );
+    }
+    rr = block_sum(rr, scratch);
+    if ( threadIdx.x == 0 ) partials[P + blockIdx.x] = rr;
+    rz = block_sum(rz, scratch);
+    if ( threadIdx.x == 0 ) partials[2 * P + blockIdx.x] = rz;
+    __threadfence();
+    grid.sync();
+    const double s0 = sum_partials(partials + P, gridDim.x, scratch);
+    __syncthreads();
+    const double s1 = sum_partials(partials + 2 * P, gridDim.x, scratch);
+    if ( threadIdx.x == 0 ) { bc[0] = s0; bc[1] = s1; }
+    __syncthreads();
+    const double t0 = bc[0], t1 = bc[1];
+    if ( blockIdx.x == 0 && threadIdx.x == 0 ) {
+        red[0] = t0; red[1] = t1;
+        S->alpha = alpha;
+        cg_scalars(2, iter, tol, red, S);               // resid test, rho_1 = rho, rho = r.z, beta     (cg.h:57-66, 47-51)
+    }
+    if ( sqrt(t0) / normb <= tol ) return;               // converged: every CTA takes the same branch
+    const double beta = t1 / rho;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < neq; i += stride ) {
+        const double z = diag ? r[i] * diag[i] : r[i];
+        p[i] = z + beta * p[i];
+    }
+}
+
 // masked dot product (distributed path: p.q after the halo sum); last CTA leaves the sum in red[0]
 __global__ void __launch_bounds__(kCgThreads)
 cg_dot_kernel(int32_t neq, const double *__restrict__ a, const double *__restrict__ b,
@@ -424,6 +494,20 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
     else OB_LAUNCH(ctx, cg_init_kernel< true >, G, kCgThreads, 0, n, b_dev, w.q, w.r, diag, owned, w.partials, P, w.red, tol, w.S);
     OB_CHECK( finish(0, 0, 3) );
 
+    // one GPU: the iteration tail as one cooperative launch, if the device can hold the whole grid at once
+    bool coop = false;
+    int coop_grid = 0;
+    if ( !comm && n > 0 && !( getenv("OB200_CG_COOP") && getenv("OB200_CG_COOP")[0] == '0' ) ) {
+        int can = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, ctx->device);
+        if ( can && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_xr_p_kernel, kCgThreads, 0) == cudaSuccess && per_sm > 0 ) {
+            coop_grid = per_sm * ctx->shape.sms;
+            if ( coop_grid > G ) coop_grid = G;
+            coop = coop_grid <= kCgMaxBlocks;
+        }
+        cudaGetLastError();
+    }
+
     CgScalars h;
     const int poll = 8;
     int it = 0;
@@ -432,7 +516,32 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
         int batch_end = it + poll < max_iter ? it + poll : max_iter;
         for ( ; it < batch_end; ) {
             it++;
-            OB_LAUNCH(ctx, cg_update_p_kernel, G, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
+            if ( !coop || it == 1 ) OB_LAUNCH(ctx, cg_update_p_kernel, G, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
+            if ( coop ) {
+                // two launches per iteration: the product with its p.q partials, then everything else
+                int nb = 0;
+                OB_CHECK( spmv_fused_dot(A, w.p, w.q, w.partials, &nb, &w.S->done) );
+                int32_t n_ = n;
+                double *x_ = x_dev, *r_ = w.r, *p_ = w.p, *q_ = w.q, *pa_ = w.partials, *red_ = w.red;
+                const double *d_ = diag, *sp_ = w.partials;
+                int P_ = P, it_ = it;
+                double tol_ = tol;
+                CgScalars *S_ = w.S;
+                void *args[] = { &n_, &x_, &r_, &p_, &q_, &d_, &sp_, &nb, &pa_, &P_, &red_, &it_, &tol_, &S_ };
+                ob200_prof_rec pr = { "cg_xr_p_kernel", nullptr, nullptr };
+                if ( ctx->profiling ) {
+                    pr.start = ctx->prof_event();
+                    pr.stop = ctx->prof_event();
+                    cudaEventRecord(pr.start, ctx->stream);
+                }
+                OB_CUDA( cudaLaunchCooperativeKernel((void *) cg_xr_p_kernel, dim3(coop_grid), dim3(kCgThreads), args, 0, ctx->stream) );
+                if ( ctx->profiling ) {
+                    cudaEventRecord(pr.stop, ctx->stream);
+                    ctx->prof_pending.push_back(pr);
+                }
+                ctx->launches++;
+                continue;
+            }
             if ( !comm ) {
                 int nb = 0;
                 OB_CHECK( spmv_fused_dot(A, w.p, w.q, w.partials, &nb, &w.S->done) );      // q = A p, partials of p.q
@@ -441,18 +550,9 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
                 // one kernel: q = A p, p.q over the rows only this rank holds, shared rows pushed to the sharers;
                 // the pull sums the sharers' values and adds p.q over the shared rows this rank owns
                 const unsigned int seq = ++comm->halo_seq;
-                static const bool fused_push = !( getenv("OB200_FUSED_PUSH") && getenv("OB200_FUSED_PUSH")[0] == '0' );
-                static const bool fake = getenv("OB200_DBG_FAKEROUTE") != nullptr;
-                static DevBuf< int32_t > fake_route;
-                if ( fake && !fake_route.p ) {
-                    OB_CHECK( fake_route.alloc(n) );
-                    OB_CUDA( cudaMemsetAsync(fake_route.p, 0xFF, sizeof( int32_t ) * (size_t) n, ctx->stream) );
-                }
-                const SpmvHalo hv{ fake ? fake_route.p : comm->route.p, comm->uniq_ptr.p, fused_push ? comm->push_dst.p : nullptr,
-                                   2 * (int64_t)( seq & 1u ) * ML.data_half, seq };
+                const SpmvHalo hv{ comm->route.p, comm->uniq_ptr.p, comm->push_dst.p, 2 * (int64_t)( seq & 1u ) * ML.data_half, seq };
                 int nb = 0;
                 OB_CHECK( spmv_fused_halo(A, w.p, w.q, w.partials, &nb, &w.S->done, hv) );
-                if ( !fused_push ) OB_CHECK( comm_p2p_push(comm, w.q, seq, &w.S->done) );
                 OB_CHECK( comm_p2p_pull(comm, w.q, seq, w.p, &w.S->done) );
                 OB_CHECK( finish(1, it, 1, w.partials, nb, comm->pull_partials.p, comm->pull_grid) );
             } else {
