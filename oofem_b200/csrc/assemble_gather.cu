@@ -730,7 +730,9 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
                 }
             }
         }
-        asm volatile( "bar.sync 1, %0;" ::"n"( kGatherThreads ) : "memory" );     // parking lot free for the next group
+        // no barrier here: the parking lot is next written in phase A2 of the following group, behind that group's
+        // A1 -> A2 barrier, which every warp reaches only after its phase B of this group; warps without a node to
+        // reduce start on the next group's geometry right away
     }
 }
 
