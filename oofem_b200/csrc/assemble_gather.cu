@@ -781,6 +781,7 @@ int gather_prepare_mesh(ob200_elemset *S)
     OB_LAUNCH(ctx, element_coords_kernel, grid, 256, 0, S->conn.p, S->coords.p, n, S->exyz.p);
     OB_CHECK( S->nodeeq.alloc(S->nnode * 3) );
     OB_CUDA( cudaMemsetAsync(S->nodeeq.p, 0, sizeof( int32_t ) * (size_t) S->nnode * 3, ctx->stream) );
+    OB_CHECK( elemset_await_loc(S) );
     OB_LAUNCH(ctx, node_equations_kernel, grid, 256, 0, S->conn.p, S->loc.p, S->nelem, S->nen, S->nodeeq.p);
     return OB200_OK;
 }

@@ -104,6 +104,10 @@ struct ob200_prof_rec {
 struct ob200_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // second stream + event for uploads that may overlap kernels of the main stream (elemset_create: the
+    // location arrays travel while the node incidence is being built from the connectivity)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_event = nullptr;
     cudaDeviceProp prop;
     ob200::LaunchShape shape;
     int64_t launches = 0;

@@ -70,6 +70,12 @@ int ob200_context_create(int device, ob200_context **out)
         delete ctx;
         return OB200_ECUDA;
     }
+    if ( cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+         cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming) != cudaSuccess ) {
+        set_error("context_create: copy stream creation failed");
+        delete ctx;
+        return OB200_ECUDA;
+    }
     ctx->shape.sms = ctx->prop.multiProcessorCount;
     // keep freed work buffers cached in the pool instead of returning them to the driver at every sync
     cudaMemPool_t pool;
@@ -94,6 +100,9 @@ void ob200_context_destroy(ob200_context *ctx)
     cudaStreamSynchronize(ctx->stream);
     stream_register(ctx->stream, false);
     if ( current_stream().stream == ctx->stream ) current_stream().stream = nullptr;
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_event);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -413,11 +413,27 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
         OB_CUDA( cudaMemcpyAsync(buf.p, src, sizeof( *src ) * (size_t) n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream) );
         return OB200_OK;
     };
-    if ( ( rc = put(S->coords, coords, nnode * 3) ) < 0 || ( rc = put(S->conn, conn, nelem * S->nen) ) < 0 ||
-         ( rc = put(S->matid, matid, nelem) ) < 0 || ( rc = put(S->mat, matparams, (int64_t) nmat * OB200_MATPARAM_STRIDE) ) < 0 ||
-         ( rc = put(S->loc, loc, nelem * S->nd) ) < 0 ) {
+    // the small tables and what the node incidence needs go first on the main stream; the location arrays
+    // (the largest upload) follow on the copy stream and are awaited where they are first read
+    if ( ( rc = put(S->mat, matparams, (int64_t) nmat * OB200_MATPARAM_STRIDE) ) < 0 || ( rc = put(S->conn, conn, nelem * S->nen) ) < 0 ||
+         ( rc = put(S->coords, coords, nnode * 3) ) < 0 || ( rc = put(S->matid, matid, nelem) ) < 0 ||
+         ( rc = S->loc.alloc(nelem * S->nd) ) < 0 ) {
         delete S;
         return rc;
+    }
+    if ( nelem > 0 ) {
+        cudaError_t e = cudaEventRecord(ctx->copy_event, ctx->stream);                 // the allocation is ordered on the main stream
+        if ( e == cudaSuccess ) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0);
+        if ( e == cudaSuccess )
+            e = cudaMemcpyAsync(S->loc.p, loc, sizeof( int32_t ) * (size_t)( nelem * S->nd ),
+                                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->copy_stream);
+        if ( e == cudaSuccess ) e = cudaEventRecord(ctx->copy_event, ctx->copy_stream);
+        if ( e != cudaSuccess ) {
+            set_error("elemset_create: upload of the location arrays failed (%s)", cudaGetErrorString(e));
+            delete S;
+            return OB200_ECUDA;
+        }
+        S->loc_pending = true;
     }
     // material state only when a MisesMat is present (host copy of the small parameter table decides)
     std::vector< double > mp( (size_t) nmat * OB200_MATPARAM_STRIDE );
@@ -440,6 +456,12 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
         }
     }
     if ( ( rc = gather_prepare_mesh(S) ) < 0 ) { delete S; return rc; }
+    if ( ( rc = elemset_await_loc(S) ) < 0 ) { delete S; return rc; }
+    if ( !on_device && cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess ) {      // the caller's host buffer is free again on return
+        set_error("elemset_create: upload of the location arrays failed");
+        delete S;
+        return OB200_ECUDA;
+    }
     if ( S->has_state ) {
         int64_t n = nelem * S->ngp * OB200_MISES_STATE_DOUBLES;
         if ( ( rc = S->state.alloc(n) ) < 0 ) { delete S; return rc; }

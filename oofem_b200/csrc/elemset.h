@@ -72,6 +72,7 @@ struct ob200_elemset {
     ob200::DevBuf< unsigned short > blk;
     ob200::DevBuf< int2 > gtab;
     bool all_isole = true;
+    bool loc_pending = false;                      // loc is still travelling on the context's copy stream
     int64_t neq_hint() const { return neq; }
     ob200::ElemSetView view() const
     {
@@ -86,6 +87,15 @@ void ob200_csr_touch(ob200_csr *A);
 int ob200_csr_materialize(ob200_csr *A);
 
 namespace ob200 {
+// make the main stream wait for the upload of loc (no-op once done)
+inline int elemset_await_loc(ob200_elemset *S)
+{
+    if ( S->loc_pending ) {
+        OB_CUDA( cudaStreamWaitEvent(S->ctx->stream, S->ctx->copy_event, 0) );
+        S->loc_pending = false;
+    }
+    return OB200_OK;
+}
 int gather_prepare_mesh(ob200_elemset *S);                       // at create: incidence, nodeeq
 int gather_bind(ob200_elemset *S, ob200_csr *A);                 // at bind: block schedule, group table
 int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A);      // the kernel
