@@ -24,6 +24,7 @@
 #include "scan.cuh"
 #include <limits.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace ob200 {
 
@@ -193,7 +194,7 @@ visit_unique_kernel(int32_t ngroups, const int2 *__restrict__ gtab, const int32_
 // flags[0]: a node's column blocks do not line up with the CSR row (free equations of a node not
 // consecutive, or the pattern is not the one of this element set); flags[1]: capacity exceeded.
 __global__ void __launch_bounds__(256)
-node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const int32_t *__restrict__ ninc,
+node_blocks_allpairs_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const int32_t *__restrict__ ninc,
                    const int32_t *__restrict__ conn, const int32_t *__restrict__ nodeeq,
                    const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int maxblk,
                    unsigned char *__restrict__ pos, unsigned char *__restrict__ nblk, unsigned short *__restrict__ blk,
@@ -331,6 +332,205 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
         }
         if ( lane == 0 ) {
             nblk[w] = (unsigned char)( row >= 0 ? nb_max : 0 );
+            // matrix entries this node's rows account for (to know whether the set covers the whole pattern)
+            if ( row >= 0 ) atomicAdd(covered, (unsigned long long) width_total * ( ( r0 > 0 ) + ( r1 > 0 ) + ( r2 > 0 ) ));
+        }
+    }
+}
+
+// The same schedule, sort-based: the warp sorts the node's items by (key, item index) with a bitonic network
+// in registers (four items per lane), which turns the ranks of the all-pairs version above into scans:
+// same_before = position - start of the run, column block = number of run starts before.  Produces exactly
+// the arrays of node_blocks_allpairs_kernel (kept as the cross-check, OB200_NODE_BLOCKS=allpairs) in ~40 % of
+// the instructions.
+__global__ void __launch_bounds__(256)
+node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const int32_t *__restrict__ ninc,
+                   const int32_t *__restrict__ conn, const int32_t *__restrict__ nodeeq,
+                   const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int maxblk,
+                   unsigned char *__restrict__ pos, unsigned char *__restrict__ nblk, unsigned short *__restrict__ blk,
+                   int *__restrict__ flags, unsigned long long *__restrict__ covered)
+{
+    const int lane = threadIdx.x & 31, ws = threadIdx.x >> 5;
+    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    constexpr int Q = 4, N = 128, NCH = N / 32;
+    static_assert( kMaxValence * 8 == N, "four items per lane" );
+    __shared__ int s_cnt[8][N], s_info[8][N], s_cstart[8][N], s_nacc[8][NCH][kMaxValence], s_cbase[8][NCH + 1];
+    __shared__ unsigned int s_ball[8][NCH][kMaxValence];
+    typedef unsigned long long u64;
+    for ( int64_t w = warp0; w < nnode; w += nwarps ) {
+        const int v0 = ninc_start[w], nv = ninc_start[w + 1] - v0;
+        const int nitems = nv * 8;
+        if ( nv > kMaxValence ) {
+            if ( lane == 0 ) atomicAdd(flags + 1, 1);
+            continue;
+        }
+        // composite sort key: equation number of the column node's first free dof | item index | free-dof mask
+        u64 v[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            const int it = q * 32 + lane;
+            int key = INT_MAX, cm = 0;
+            if ( it < nitems ) {
+                const int e = ninc[v0 + ( it >> 3 )] >> 3;
+                const int nb = conn[(int64_t) e * 8 + ( it & 7 )] - 1;
+                const int e0 = nodeeq[(int64_t) nb * 3], e1 = nodeeq[(int64_t) nb * 3 + 1], e2 = nodeeq[(int64_t) nb * 3 + 2];
+                cm = ( e0 > 0 ? 1 : 0 ) | ( e1 > 0 ? 2 : 0 ) | ( e2 > 0 ? 4 : 0 );
+                if ( cm ) key = e0 > 0 ? e0 : ( e1 > 0 ? e1 : e2 );
+                // free equations of a node must be consecutive for its columns to form one block
+                int prev = 0, ok = 1;
+                if ( e0 > 0 ) prev = e0;
+                if ( e1 > 0 ) { if ( prev && e1 != prev + 1 ) ok = 0; prev = e1; }
+                if ( e2 > 0 ) { if ( prev && e2 != prev + 1 ) ok = 0; }
+                if ( !ok ) atomicAdd(flags, 1);
+            }
+            v[q] = ( (u64) (unsigned int) key << 16 ) | ( (u64) it << 8 ) | (u64) cm;
+        }
+        // bitonic sort, ascending; element e = 4 * lane + q
+#define OB_CE(a, b, up)                           \
+    {                                             \
+        const u64 lo__ = a < b ? a : b, hi__ = a < b ? b : a; \
+        a = ( up ) ? lo__ : hi__;                 \
+        b = ( up ) ? hi__ : lo__;                 \
+    }
+#pragma unroll
+        for ( int k = 2; k <= N; k <<= 1 ) {
+#pragma unroll
+            for ( int j = k >> 1; j > 0; j >>= 1 ) {
+                if ( j >= 4 ) {
+                    const int lj = j >> 2;
+                    const bool lower = ( lane & lj ) == 0;
+                    const bool up = ( ( lane * 4 ) & k ) == 0;
+#pragma unroll
+                    for ( int q = 0; q < Q; q++ ) {
+                        const u64 o = __shfl_xor_sync(0xffffffffu, v[q], lj);
+                        const u64 mn = v[q] < o ? v[q] : o, mx = v[q] < o ? o : v[q];
+                        v[q] = ( lower == up ) ? mn : mx;
+                    }
+                } else if ( j == 2 ) {
+                    const bool up = ( ( lane * 4 ) & k ) == 0;
+                    OB_CE(v[0], v[2], up);
+                    OB_CE(v[1], v[3], up);
+                } else {
+                    const bool up01 = ( ( lane * 4 ) & k ) == 0, up23 = ( ( lane * 4 + 2 ) & k ) == 0;
+                    OB_CE(v[0], v[1], up01);
+                    OB_CE(v[2], v[3], up23);
+                }
+            }
+        }
+#undef OB_CE
+        int key[Q], item[Q], cm[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            key[q] = (int)( v[q] >> 16 );
+            item[q] = (int)( ( v[q] >> 8 ) & 0xFF );
+            cm[q] = (int)( v[q] & 0xFF );
+        }
+        // runs of equal keys
+        int prevk = __shfl_up_sync(0xffffffffu, key[Q - 1], 1);
+        if ( lane == 0 ) prevk = -1;
+        bool start[Q], valid[Q];
+        int rs[Q], bi[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            start[q] = key[q] != ( q == 0 ? prevk : key[q - 1] );
+            valid[q] = key[q] != INT_MAX;
+        }
+        {   // start of my run (inclusive max-scan of the start positions), my column block (inclusive count of starts - 1)
+            int loc = -1, cntl = 0;
+#pragma unroll
+            for ( int q = 0; q < Q; q++ ) {
+                if ( start[q] ) loc = lane * 4 + q;
+                if ( start[q] && valid[q] ) cntl++;
+                rs[q] = loc;
+                bi[q] = cntl;
+            }
+            int incl = loc, csum = cntl;
+#pragma unroll
+            for ( int o = 1; o < 32; o <<= 1 ) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, csum, o);
+                if ( lane >= o ) { incl = max(incl, t); csum += u; }
+            }
+            int cin = __shfl_up_sync(0xffffffffu, incl, 1), bin = __shfl_up_sync(0xffffffffu, csum, 1);
+            if ( lane == 0 ) { cin = -1; bin = 0; }
+#pragma unroll
+            for ( int q = 0; q < Q; q++ ) {
+                rs[q] = max(rs[q], cin);
+                bi[q] = bin + bi[q] - 1;
+            }
+        }
+        const int ndist = __shfl_sync(0xffffffffu, bi[Q - 1] + 1, 31);        // valid run starts in the whole warp
+        int *cnt = s_cnt[ws], *info = s_info[ws], *cst = s_cstart[ws];
+        __syncwarp();
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) cnt[q * 32 + lane] = 0;
+        __syncwarp();
+        int sb[Q];
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            sb[q] = lane * 4 + q - rs[q];
+            if ( valid[q] ) {
+                atomicMax(&cnt[bi[q]], sb[q] + 1);
+                if ( start[q] ) info[bi[q]] = __popc(cm[q]) | ( cm[q] << 8 );
+            }
+        }
+        __syncwarp();
+        // per column block (lane = block, 32 at a time): first column, and the jagged-diagonal bookkeeping
+        int wcarry = 0, ccarry = 0;
+        for ( int c = 0; c * 32 < ndist; c++ ) {
+            const int b = c * 32 + lane;
+            const int cb = b < ndist ? cnt[b] : 0, wb = b < ndist ? ( info[b] & 0xFF ) : 0;
+            int incl = wb;
+#pragma unroll
+            for ( int o = 1; o < 32; o <<= 1 ) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ( lane >= o ) incl += t;
+            }
+            if ( b < ndist ) cst[b] = wcarry + incl - wb;
+            wcarry += __shfl_sync(0xffffffffu, incl, 31);
+            int run = 0;
+            for ( int i = 0; i < kMaxValence; i++ ) {
+                const unsigned int m = __ballot_sync(0xffffffffu, cb > i);
+                if ( lane == 0 ) {
+                    s_ball[ws][c][i] = m;
+                    s_nacc[ws][c][i] = run;
+                }
+                run += __popc(m);
+                if ( m == 0 ) break;
+            }
+            if ( lane == 0 ) s_cbase[ws][c] = ccarry;
+            ccarry += run;
+        }
+        __syncwarp();
+        // the node's own rows (any free dof; all of them share the pattern)
+        const int r0 = nodeeq[w * 3], r1 = nodeeq[w * 3 + 1], r2 = nodeeq[w * 3 + 2];
+        const int row = r0 > 0 ? r0 - 1 : ( r1 > 0 ? r1 - 1 : ( r2 > 0 ? r2 - 1 : -1 ) );
+#pragma unroll
+        for ( int q = 0; q < Q; q++ ) {
+            if ( item[q] >= nitems ) continue;
+            const bool live = valid[q] && row >= 0;
+            int park = 0xFF;
+            if ( live ) {
+                const int B = bi[q], c = B >> 5, i = sb[q];
+                park = s_cbase[ws][c] + s_nacc[ws][c][i] + __popc(s_ball[ws][c][i] & ( ( 1u << ( B & 31 ) ) - 1u ));
+                const int cb = cnt[B];
+                if ( park >= 0xFF || B >= maxblk || cb > 0xFF ) atomicAdd(flags + 1, 1);
+                if ( start[q] && B < maxblk ) {
+                    // one entry per column block: number of parked items, free-dof mask of the column node
+                    blk[w * maxblk + B] = (unsigned short)( cb | ( cm[q] << 8 ) );
+                    if ( colind[rowptr[row] + cst[B]] != key[q] - 1 ) atomicAdd(flags, 1);
+                }
+            }
+            pos[( (int64_t) v0 + ( item[q] >> 3 ) ) * 8 + ( item[q] & 7 )] = (unsigned char) park;
+        }
+        const int nb_max = row >= 0 ? ndist : 0, width_total = row >= 0 ? wcarry : 0;
+        if ( row >= 0 ) {
+            if ( width_total != rowptr[row + 1] - rowptr[row] || width_total > kMaxRowLen ) {
+                if ( lane == 0 ) atomicAdd(flags + ( width_total > kMaxRowLen ? 1 : 0 ), 1);
+            }
+        }
+        if ( lane == 0 ) {
+            nblk[w] = (unsigned char) nb_max;
             // matrix entries this node's rows account for (to know whether the set covers the whole pattern)
             if ( row >= 0 ) atomicAdd(covered, (unsigned long long) width_total * ( ( r0 > 0 ) + ( r1 > 0 ) + ( r2 > 0 ) ));
         }
@@ -801,9 +1001,16 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     OB_CHECK( flags.alloc(4) );            // [0] mismatch, [1] capacity, [2..3] 64-bit count of covered entries
     OB_CUDA( cudaMemsetAsync(flags.p, 0, sizeof( int ) * 4, ctx->stream) );
     OB_CUDA( cudaMemsetAsync(S->blk.p, 0, sizeof( unsigned short ) * (size_t) S->nnode * S->maxblk, ctx->stream) );
-    OB_LAUNCH(ctx, node_blocks_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
-              S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
-              reinterpret_cast< unsigned long long * >( flags.p + 2 ));
+    static const bool allpairs = getenv("OB200_NODE_BLOCKS") && !strcmp(getenv("OB200_NODE_BLOCKS"), "allpairs");
+    if ( allpairs ) {
+        OB_LAUNCH(ctx, node_blocks_allpairs_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
+                  S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
+                  reinterpret_cast< unsigned long long * >( flags.p + 2 ));
+    } else {
+        OB_LAUNCH(ctx, node_blocks_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
+                  S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
+                  reinterpret_cast< unsigned long long * >( flags.p + 2 ));
+    }
     int h[4] = { 0, 0, 0, 0 };
     OB_CUDA( cudaMemcpyAsync(h, flags.p, sizeof( int ) * 4, cudaMemcpyDeviceToHost, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
