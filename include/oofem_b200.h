@@ -177,6 +177,7 @@ int  ob200_comm_set_halo(ob200_comm *c, int32_t neq, int nneigh, const int32_t *
 int  ob200_comm_p2p_export(ob200_comm *c, int64_t cap, void *handle64);
 int  ob200_comm_p2p_open(ob200_comm *c, const void *handles);
 int  ob200_comm_p2p_enabled(const ob200_comm *c);
+int  ob200_comm_p2p_disable(ob200_comm *c);   /* all ranks, if _open failed on any of them: NCCL stays in use */
 /* y <- y + contributions of the neighbours for shared dofs (OOFEM: updateSharedDofManagers) */
 int  ob200_comm_exchange_add(ob200_comm *c, double *y_dev);
 /* distributed PCG: A is the local sub-assembled matrix of this partition, b must already

@@ -78,6 +78,7 @@ SYMBOLS = {
     "ob200_comm_p2p_export": (_int, [_vp, C.c_int64, _vp]),
     "ob200_comm_p2p_open": (_int, [_vp, _vp]),
     "ob200_comm_p2p_enabled": (_int, [_vp]),
+    "ob200_comm_p2p_disable": (_int, [_vp]),
     "ob200_cg_solve_dist": (_int, [_vp, _vp, _vp, _vp, _int, _int, _dbl, C.POINTER(_int), C.POINTER(_dbl), _int]),
 }
 

@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -78,9 +79,12 @@ class Comm:
         flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
-            # some rank could not map: nobody may use the mailboxes
-            raise RuntimeError("peer-memory transport could not be mapped on every rank; set OB200_P2P=0 to use NCCL: "
-                               + lib().ob200_last_error().decode())
+            # some rank could not map: nobody may use the mailboxes, the NCCL transport stays in use
+            lib().ob200_comm_p2p_disable(self.h)
+            if self.rank == 0:
+                print("oofem_b200: peer-memory transport not available on every rank (%s); using NCCL"
+                      % lib().ob200_last_error().decode(), file=sys.stderr)
+            return False
         return True
 
     @property

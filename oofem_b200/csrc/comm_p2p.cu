@@ -259,4 +259,12 @@ int ob200_comm_p2p_open(ob200_comm *c, const void *handles)
 
 int ob200_comm_p2p_enabled(const ob200_comm *c) { return c && c->p2p ? 1 : 0; }
 
+/* collective decision of the caller: some rank could not map -> every rank goes back to the NCCL transport */
+int ob200_comm_p2p_disable(ob200_comm *c)
+{
+    OB_REQUIRE(c, OB200_EINVAL, "comm_p2p_disable: null communicator");
+    c->p2p = false;
+    return OB200_OK;
+}
+
 } // extern "C"
