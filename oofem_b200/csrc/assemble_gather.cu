@@ -46,7 +46,11 @@ constexpr int kMaxRowLen = 128;                      // longest row the column-b
 constexpr int kBlkDoubles = 10;                      // a parked 3x3 block, padded to 80 B (16-byte aligned)
 constexpr int kRoundElems = OB200_ROUND_ELEMS;                    // distinct elements whose gradients are resident at a time
 constexpr int kGpStride = 26;                        // doubles per (element, Gauss point): 24 + pad (208 B: conflict-free 16-byte stores)
-constexpr int kElStride = 8 * kGpStride + 2;         // doubles per element (1680 B: neighbouring elements land in different banks)
+#ifndef OB200_EL_PAD
+#define OB200_EL_PAD 8
+#endif
+constexpr int kElStride = 8 * kGpStride + OB200_EL_PAD;   // doubles per element: 1728 B = 64 mod 128, so the two visits a quarter-warp
+                                                           // serves in phase A2 (elements 1 or 3 apart in the group's list) read disjoint banks (pad 2: 3.11 ms, pad 8: 2.93 ms)
 
 // ---- mesh-only preprocessing (elemset create) ---------------------------------------------
 
