@@ -114,8 +114,21 @@ class ClockSampler:
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------
 
-def reference_sample(dims, cg_iters, repeats, prefer_omp=True):
-    """Time the UNMODIFIED reference (oracle/_ref/oofem_bench[_omp]) on a bounded sample."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def workload_name(nx, ny, nz):
+    return (f"synthetic structured {nx}x{ny}x{nz} = {nx * ny * nz} hex LSpace isotropic linear elastic "
+            f"cantilever per GPU, FP64 PCG (BASELINE.json configs[1])")
+
+
+def reference_sample(dims, cg_iters, repeats, warmup=0, sample=0, prefer_omp=True):
+    """Time the UNMODIFIED reference (oracle/_ref/oofem_bench[_omp]) on the mesh `dims`; with sample > 0 every
+    repeat is a bounded sample (a window of `sample` elements + cg_iters CG iterations) of the work on that mesh."""
     from oofem_b200 import meshgen
     from oofem_b200.inputfile import DirichletBC, Material, NodalLoad, Problem, write_input
     nx, ny, nz = dims
@@ -137,8 +150,13 @@ def reference_sample(dims, cg_iters, repeats, prefer_omp=True):
         fn = os.path.join(td, "s.in")
         write_input(fn, pb)
         env = dict(os.environ)
-        env.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
-        r = subprocess.run([exe, fn, str(cg_iters), str(repeats)], cwd=td, capture_output=True, text=True, env=env)
+        # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for N > 1)
+        env["OMP_NUM_THREADS"] = str(host_cores())
+        env.pop("OMP_PROC_BIND", None)
+        r = subprocess.run([exe, fn, str(cg_iters), str(repeats), str(warmup), str(sample)], cwd=td, capture_output=True,
+                           text=True, env=env)
+        if r.returncode:
+            sys.stderr.write(r.stdout[-2000:] + r.stderr[-2000:])
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if r.returncode or not line:
         return None
@@ -148,34 +166,54 @@ def reference_sample(dims, cg_iters, repeats, prefer_omp=True):
 
 
 def run_reference(args):
+    """Reference arm: the UNMODIFIED reference (oracle/_ref, its own _OPENMP build on all host threads) on the SAME
+    mesh as our arm (one GPU's share of the weak-scaling workload).  Parsing the 1M-element input, building CompCol
+    and one full EngngModel::assemble are done once outside the steps; each of the K timed steps is a bounded sample
+    of the work on that mesh (a window of REF_SAMPLE_ELEMS elements through the loop body of EngngModel::assemble and
+    REF_SAMPLE_CG IML CG iterations on the full matrix), so that the whole run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    dims = (40, 20, 20)
-    repeats = max(1, min(args.steps, 3))
+    dims = (args.nx, args.ny, args.nz)
+    nel = dims[0] * dims[1] * dims[2]
+    sample = min(args.ref_sample_elems, nel)
+    cg_sample = min(args.ref_sample_cg, args.cg_iters)
     t0 = time.time()
-    res = reference_sample(dims, args.cg_iters, repeats)
-    if res is None:      # reference binary not built here: time the C port of the same algorithm
-        res = oracle_sample(dims, args.cg_iters)
+    res = reference_sample(dims, cg_sample, args.steps, args.warmup, sample if sample < nel else 0)
+    if res is None:      # reference binary not built here: time the C port of the same algorithm on a small mesh
+        res = oracle_sample((40, 20, 20), cg_sample)
         kind = "port"
+        same = False
     else:
         kind = "reference"
+        same = True
     ms = (res["t_assemble_s"] + res["t_cg_s"]) * 1e3
+    nnz = res["nnz"]
+    sample_txt = (f"mesh {dims[0]}x{dims[1]}x{dims[2]} = {res['nelem']} LSpace elements, neq {res['neq']}, nnz {nnz} (the "
+                  f"full configuration); per step: {res.get('sample_elements', res['nelem'])} consecutive elements through "
+                  f"TangentAssembler::matrixFromElement + CompCol::assemble (loop body of EngngModel::assemble, its OpenMP "
+                  f"pragmas) and {cg_sample} IML CG iterations (DiagPreconditioner) on the full matrix; the reference's own "
+                  f"EngngModel::assemble over all elements, timed once: {res.get('t_assemble_full_s', float('nan')):.2f} s = "
+                  f"{res.get('elements_per_s_full', float('nan')):.0f} elements/s; CompCol::buildInternalStructure "
+                  f"{res.get('t_structure_s', float('nan')):.1f} s, input parse {res.get('t_parse_s', float('nan')):.1f} s "
+                  f"(both outside the steps)") if same else \
+                 f"oracle port on 40x20x20 = {res['nelem']} elements (reference binary absent)"
     line = {
         "impl": "reference", "metric": "elements assembled/s", "value": res["elements_per_s"], "unit": "elements/s",
-        "pcg_iters_per_s": res["cg_iters_per_s"], "n_gpus": args.gpus, "steps": repeats, "warmup": 0,
+        "pcg_iters_per_s": res["cg_iters_per_s"], "pcg_nnz_iters_per_s": res["cg_iters_per_s"] * nnz,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "synthetic structured 1M-hex LSpace isotropic linear elastic beam, FP64 PCG "
-                               "(BASELINE.json configs[1]); reference arm runs a bounded sample of it",
-                   "sample": f"{dims[0]}x{dims[1]}x{dims[2]} hex = {res['nelem']} elements, neq {res['neq']}, "
-                             f"nnz {res['nnz']}, {args.cg_iters} CG iterations", "cg_iters_per_step": args.cg_iters},
+        "config": {"workload": workload_name(*dims) if same else "bounded 40x20x20 sample of " + workload_name(*dims),
+                   "nelem_per_gpu": res["nelem"], "neq_per_gpu": res["neq"], "nnz_per_gpu": nnz,
+                   "cg_iters_per_step": args.cg_iters, "precond": "diag"},
         "cpu_baseline": {"value": res["elements_per_s"], "unit": "elements/s", "pcg_iters_per_s": res["cg_iters_per_s"],
-                         "cores": res.get("threads", 1), "kind": kind,
-                         "sample": f"{res['nelem']} LSpace elements assembled by EngngModel::assemble into CompCol; "
-                                   f"{args.cg_iters} IML CG iterations at nnz {res['nnz']}"},
+                         "cores": res.get("threads", 1), "kind": kind, "sample": sample_txt},
         "e2e": {"value": res["elements_per_s"], "unit": "elements/s", "pcg_iters_per_s": res["cg_iters_per_s"],
                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_detail": {k: res.get(k) for k in ("t_parse_s", "t_structure_s", "t_assemble_full_s", "elements_per_s_full",
+                                                     "sample_elements", "t_assemble_s", "t_assemble_best_s", "t_cg_s",
+                                                     "t_cg_best_s", "cg_iters", "threads", "exe")},
         "wall_s": time.time() - t0,
     }
     print(json.dumps(line))
@@ -354,11 +392,28 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_asm, e_cg = [float(v) for v in te.cpu()]
 
+    # ---- multi-GPU parity (checker leg, after every timed region): small partitioned problems against the serial
+    # oracle -- LSpace and LTRSpace, x-slabs and box partitions (dofs shared by 4 / 8 ranks), both transports
+    parity, parity_ok = None, True
+    if dist and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import dist_cases
+        S.close()
+        cases = dist_cases.run_all(ctx, dev)
+        parity_ok = all(c["ok"] for c in cases)
+        parity = {"ok": parity_ok, "tolerance": {"spmv_relerr": dist_cases.SPMV_TOL, "u_relerr": dist_cases.U_TOL},
+                  "spmv_relerr": max(c["spmv_relerr"] for c in cases), "u_relerr": max(c["u_relerr"] for c in cases),
+                  "max_sharers": max(c["max_sharers"] for c in cases),
+                  "transport": sorted(set(c["transport_used"] for c in cases)),
+                  "oracle": "serial C restatement of the reference (oracle/oofem_oracle.c) on the unpartitioned mesh",
+                  "cases": [{k: c[k] for k in ("etype", "partition", "transport", "transport_used", "ok", "spmv_relerr", "u_relerr",
+                                               "iters", "iters_equal_on_all_ranks", "max_sharers", "neq_global")} for c in cases]}
+
     if rank != 0:
         if dist:
             dist.barrier()
             dist.destroy_process_group()
-        return 0
+        return 0 if parity_ok else 1
 
     # ---- roofline of the dominant kernel ---------------------------------------------
     peak, peak_src = load_peaks()
@@ -397,7 +452,7 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = reference_sample((40, 20, 20), 20, 1)
+        cpu = reference_sample((40, 20, 20), 20, 1, 0, 0)
         kind = "reference"
         if cpu is None:
             cpu = oracle_sample((40, 20, 20), 20)
@@ -406,11 +461,11 @@ def run_ours(args):
     line = {
         "metric": "elements assembled/s", "value": total_elems / (t_asm * 1e-3), "unit": "elements/s",
         "pcg_iters_per_s": args.cg_iters / (t_cg * 1e-3),
+        "pcg_nnz_iters_per_s": args.cg_iters / (t_cg * 1e-3) * float(nnz) * world,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
         "ms_assembly": t_asm, "ms_pcg": t_cg,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic structured {nx}x{ny}x{nz} = {nelem} hex LSpace isotropic linear elastic "
-                               f"cantilever per GPU, FP64 PCG (BASELINE.json configs[1])",
+        "config": {"workload": workload_name(nx, ny, nz),
                    "nelem_per_gpu": nelem, "neq_per_gpu": neq, "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
                    "precond": "diag", "partition": f"{world} x-slabs, shared-plane halo" if world > 1 else "none",
                    "transport": ("peer memory (CUDA IPC mailboxes over NVLink)" if comm.p2p else "NCCL") if comm else "none",
@@ -418,6 +473,8 @@ def run_ours(args):
                    "structure_build_s": round(t_structure, 4)},
         "roofline": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                      "frac": spmv_gbs / peak, "traffic": spmv_traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
+                                       "committed ncu --set full capture of this kernel at this size; not measured in this run",
                      "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_dur * 1e3, "launches": n_spmv,
                      "timing": "CUDA events around every launch, second pass of the same steps right after the timed pass",
                      "index": ("blocked: %d row blocks, %d column blocks for %d non-zeros; plain CSR would read %.3f GB "
@@ -439,12 +496,16 @@ def run_ours(args):
                                 "cores": cpu.get("threads", 1), "kind": kind,
                                 "sample": f"{cpu['nelem']} LSpace elements (40x20x20 sample of the same beam) assembled by the "
                                           f"reference's EngngModel::assemble into CompCol; 20 IML CG iterations at nnz {cpu['nnz']}"}
+    if parity is not None:
+        line["parity"] = parity
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    if not parity_ok:
+        sys.stderr.write("bench.py: multi-GPU parity FAILED: %s\n" % json.dumps(parity))
+    return 0 if parity_ok else 1
 
 
 def main():
@@ -457,6 +518,9 @@ def main():
     ap.add_argument("--ny", type=int, default=64)
     ap.add_argument("--nz", type=int, default=64)
     ap.add_argument("--cg-iters", type=int, default=50)
+    ap.add_argument("--ref-sample-elems", type=int, default=32000, help="reference arm: elements assembled per timed step")
+    ap.add_argument("--ref-sample-cg", type=int, default=5, help="reference arm: CG iterations per timed step")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the multi-GPU parity cases after the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu profiling runs only)")
     ap.add_argument("--no-kernel-events", action="store_true", help="scratch: no per-kernel CUDA events in the timed region (no roofline)")

@@ -438,6 +438,8 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
     const unsigned char *owned = comm ? comm->owned.p : nullptr;
     const bool dist = comm && comm->nranks > 1;
 
+    // a pending lazy zero() must be visible to the preconditioner set-up below (it reads val directly)
+    OB_CHECK( ob200_csr_materialize(A) );
     // preconditioner (IMLSolver::solve re-inits when the matrix version changed, imlsolver.C:110-114)
     const double *diag = nullptr;
     if ( precond == OB200_PRECOND_DIAG ) {

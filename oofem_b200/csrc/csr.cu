@@ -484,6 +484,10 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
     OB_REQUIRE(hflag[1] == 0, OB200_ECAPACITY, "csr_build_structure: internal row buffer overflow");
     A->neq = neq;
     A->nnz = nnz;
+    {
+        static int64_t structure_counter = 0;
+        A->structure_version = __atomic_add_fetch(&structure_counter, 1, __ATOMIC_RELAXED);
+    }
     A->version++;
     A->diag_version = -1;
     A->zero_pending = false;

@@ -539,7 +539,7 @@ int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
     OB_CHECK( gather_bind(S, A) );
     if ( !S->gather_ok ) OB_CHECK( build_slot_map(S, A) );
     S->bound = A;
-    S->bound_version = ob200_csr_rows(A);
+    S->bound_version = A->structure_version;
     return OB200_OK;
 }
 
@@ -547,7 +547,7 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
 {
     if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && A, OB200_EINVAL, "elemset_assemble_stiffness: null argument");
-    if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
+    if ( S->bound != A || S->bound_version != A->structure_version ) OB_CHECK( ob200_elemset_bind(S, A) );
     if ( S->gather_ok ) {
         if ( S->nelem ) OB_CHECK( gather_assemble_lspace(S, A) );
         ob200_csr_touch(A);
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(256) probe_scatter_kernel(const int32_t *__res
 extern "C" int ob200_debug_probe_scatter(ob200_elemset *S, ob200_csr *A, int mode, int blocks_per_sm)
 {
     if ( S ) ob200::bind_stream(S->ctx);
-    if ( S->bound != A ) OB_CHECK( ob200_elemset_bind(S, A) );
+    if ( S->bound != A || S->bound_version != A->structure_version ) OB_CHECK( ob200_elemset_bind(S, A) );
     OB_CHECK( build_slot_map(S, A) );
     const int32_t *rowptr, *colind;
     double *val;

@@ -25,6 +25,9 @@ struct ob200_csr {
     int32_t neq = 0;
     int64_t nnz = 0;
     int64_t version = 0;
+    // identity of the sparsity structure: a process-wide counter value taken by every build_structure (never reused,
+    // so an element set bound to an earlier structure -- or to a destroyed matrix at the same address -- rebinds)
+    int64_t structure_version = 0;
     ob200::DevBuf< int32_t > rowptr, colind;     // colind / val padded by kCsrPad entries (16-byte TMA granules)
     ob200::DevBuf< double > val;
     // streamed SpMV (spmv.cuh): per-chunk {first row, first entry}

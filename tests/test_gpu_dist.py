@@ -1,5 +1,7 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): element partitions + NCCL halo
-exchange + distributed PCG against the serial oracle.  See tests/dist_worker.py."""
+"""Multi-GPU parity (needs >= 2 / 4 GPUs on the box; skipped otherwise): element partitions (slabs and boxes
+with dofs shared by >= 4 ranks), LSpace and LTRSpace, halo exchange + distributed PCG over both transports against
+the serial oracle.  See tests/dist_cases.py.  bench.py runs the same cases after its timed region when
+WORLD_SIZE > 1, so the driver's scaling runs carry the evidence even when this box has one GPU."""
 import json
 import os
 import subprocess
@@ -12,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_distributed_assembly_halo_and_pcg_vs_oracle(world, transport):
     import torch
     if torch.cuda.device_count() < world:
@@ -24,5 +26,8 @@ def test_distributed_assembly_halo_and_pcg_vs_oracle(world, transport):
                        env=dict(os.environ, OB200_P2P="1" if transport == "p2p" else "0"))
     import re
     lines = [json.loads(m) for m in re.findall(r"\{[^{}]*\}", r.stdout)]      # ranks may share a line
-    assert r.returncode == 0 and len(lines) == world and all(l["ok"] for l in lines), (r.stdout[-3000:], r.stderr[-3000:])
-    assert all(l["p2p"] == (transport == "p2p") for l in lines), lines
+    # four cases (LSpace / LTRSpace x slab / box), one line each from rank 0
+    assert r.returncode == 0 and len(lines) == 4 and all(l["ok"] for l in lines), (r.stdout[-3000:], r.stderr[-3000:])
+    assert all(l["transport_used"] == transport for l in lines), lines
+    if world >= 4:
+        assert max(l["max_sharers"] for l in lines) >= 4, lines
