@@ -352,7 +352,7 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
                    const int32_t *__restrict__ conn, const int32_t *__restrict__ nodeeq,
                    const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int maxblk,
                    unsigned char *__restrict__ pos, unsigned char *__restrict__ nblk, unsigned short *__restrict__ blk,
-                   int *__restrict__ flags, unsigned long long *__restrict__ covered)
+                   int *__restrict__ flags, unsigned long long *__restrict__ covered, unsigned char *__restrict__ ebidx)
 {
     const int lane = threadIdx.x & 31, ws = threadIdx.x >> 5;
     const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
@@ -525,7 +525,13 @@ node_blocks_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const 
                     if ( colind[rowptr[row] + cst[B]] != key[q] - 1 ) atomicAdd(flags, 1);
                 }
             }
-            pos[( (int64_t) v0 + ( item[q] >> 3 ) ) * 8 + ( item[q] & 7 )] = (unsigned char) park;
+            if ( pos ) pos[( (int64_t) v0 + ( item[q] >> 3 ) ) * 8 + ( item[q] & 7 )] = (unsigned char) park;
+            if ( ebidx ) {
+                // element-major copy for the cluster assembly (assemble_cluster.cu): index of the column block of local
+                // node b in the block list of local node a's rows, 0xFF if there is no such block
+                const int vis = ninc[v0 + ( item[q] >> 3 )];
+                ebidx[(int64_t) vis * 8 + ( item[q] & 7 )] = (unsigned char)( live && bi[q] < 0xFF ? bi[q] : 0xFF );
+            }
         }
         const int nb_max = row >= 0 ? ndist : 0, width_total = row >= 0 ? wcarry : 0;
         if ( row >= 0 ) {
@@ -1005,6 +1011,7 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     OB_CHECK( flags.alloc(4) );            // [0] mismatch, [1] capacity, [2..3] 64-bit count of covered entries
     OB_CUDA( cudaMemsetAsync(flags.p, 0, sizeof( int ) * 4, ctx->stream) );
     OB_CUDA( cudaMemsetAsync(S->blk.p, 0, sizeof( unsigned short ) * (size_t) S->nnode * S->maxblk, ctx->stream) );
+    OB_CHECK( S->ebidx.alloc(S->nvisit * 8) );
     static const bool allpairs = getenv("OB200_NODE_BLOCKS") && !strcmp(getenv("OB200_NODE_BLOCKS"), "allpairs");
     if ( allpairs ) {
         OB_LAUNCH(ctx, node_blocks_allpairs_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
@@ -1013,7 +1020,7 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     } else {
         OB_LAUNCH(ctx, node_blocks_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
                   S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
-                  reinterpret_cast< unsigned long long * >( flags.p + 2 ));
+                  reinterpret_cast< unsigned long long * >( flags.p + 2 ), S->ebidx.p);
     }
     int h[4] = { 0, 0, 0, 0 };
     OB_CUDA( cudaMemcpyAsync(h, flags.p, sizeof( int ) * 4, cudaMemcpyDeviceToHost, ctx->stream) );
@@ -1024,6 +1031,7 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     unsigned long long cov;
     memcpy(&cov, h + 2, sizeof( cov ));
     S->covers_all = ( (int64_t) cov == A->nnz );
+    if ( S->gather_ok && !allpairs ) OB_CHECK( cluster_bind(S, A) );
     return OB200_OK;
 }
 

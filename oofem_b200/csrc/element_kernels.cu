@@ -549,7 +549,7 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
     OB_REQUIRE(S && A, OB200_EINVAL, "elemset_assemble_stiffness: null argument");
     if ( S->bound != A || S->bound_version != A->structure_version ) OB_CHECK( ob200_elemset_bind(S, A) );
     if ( S->gather_ok ) {
-        if ( S->nelem ) OB_CHECK( gather_assemble_lspace(S, A) );
+        if ( S->nelem ) OB_CHECK( S->cluster_ok ? cluster_assemble_lspace(S, A) : gather_assemble_lspace(S, A) );
         ob200_csr_touch(A);
         return OB200_OK;
     }

@@ -74,6 +74,13 @@ struct ob200_elemset {
     ob200::DevBuf< unsigned char > pos, nblk, vu;
     ob200::DevBuf< unsigned short > blk;
     ob200::DevBuf< int2 > gtab;
+    // cluster assembly (assemble_cluster.cu): schedule built per bound matrix
+    bool cluster_ok = false;
+    int32_t nclusters = 0;
+    int64_t cl_nrec = 0;
+    ob200::DevBuf< unsigned char > ebidx, nloc, cl_recs, cl_steps;
+    ob200::DevBuf< unsigned short > nbase;
+    ob200::DevBuf< int32_t > cnodes, ncl, cl_begin, cl_step;
     bool all_isole = true;
     bool loc_pending = false;                      // loc is still travelling on the context's copy stream
     int64_t neq_hint() const { return neq; }
@@ -102,4 +109,6 @@ inline int elemset_await_loc(ob200_elemset *S)
 int gather_prepare_mesh(ob200_elemset *S);                       // at create: incidence, nodeeq
 int gather_bind(ob200_elemset *S, ob200_csr *A);                 // at bind: block schedule, group table
 int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A);      // the kernel
+int cluster_bind(ob200_elemset *S, ob200_csr *A);                // assemble_cluster.cu: cluster schedule (after gather_bind)
+int cluster_assemble_lspace(ob200_elemset *S, ob200_csr *A);     // assemble_cluster.cu: the kernel
 }

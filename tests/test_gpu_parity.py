@@ -150,11 +150,17 @@ def test_full_path_vs_oracle(ctx, etype, dims):
     assert relerr(ug, sol["u"]) < TOL_U
 
 
-def test_gather_assembly_irregular_numbering_vs_oracle(ctx):
-    """The owner-computes assembly on a mesh whose node and element numbers are random: a group of
+@pytest.mark.parametrize("path", ["cluster", "gather"])
+def test_gather_assembly_irregular_numbering_vs_oracle(ctx, path, monkeypatch):
+    """Both owner-computes kernels (OB200_ASSEMBLY=gather selects the round-1 kernel, the default is the cluster kernel
+    of assemble_cluster.cu) on a mesh whose node and element numbers are random: a group of
     consecutive nodes then touches unrelated elements (more distinct elements than one geometry round
     holds, element lists of a node in arbitrary order), two materials, and a second assembly that
     accumulates on top of the first (SparseMtrx::assemble adds)."""
+    if path == "gather":
+        monkeypatch.setenv("OB200_ASSEMBLY", "gather")
+    else:
+        monkeypatch.delenv("OB200_ASSEMBLY", raising=False)
     pb = _random_problem("lspace", 9, 5, 4, seed=11, mat=Material("isole", 210e3, 0.3))
     rng = np.random.default_rng(7)
     nnode, nelem = pb.coords.shape[0], pb.conn.shape[0]
@@ -186,7 +192,8 @@ def test_gather_assembly_irregular_numbering_vs_oracle(ctx):
     assert relerr(A.values(), 2.0 * val_o) < TOL_KE
     ctx.set_profiling(False)
     prof = ctx.profile_report()
-    assert prof.get("lspace_gather_kernel< false >", (0, 0))[1] == 1 and prof.get("lspace_gather_kernel< true >", (0, 0))[1] == 1, prof
+    kname = "lspace_cluster_kernel" if path == "cluster" else "lspace_gather_kernel"
+    assert prof.get(kname + "< false >", (0, 0))[1] == 1 and prof.get(kname + "< true >", (0, 0))[1] == 1, prof
     sol = orc.solve_linear_static(pb)
     ug = LinearStatic(ctx, pb).solveYourselfAt(1.0)
     assert relerr(ug, sol["u"]) < TOL_U
