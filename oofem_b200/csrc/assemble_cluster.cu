@@ -45,23 +45,40 @@ constexpr int kClBlocks = 1728;              // most 3x3 blocks (positions per p
 constexpr int kClMaxValence = 16;            // elements around a node
 constexpr int kClVisits = kClNodes * kClMaxValence;      // most (node, element) incidences of a cluster
 constexpr int kClMaxCell = 2048;             // most nodes in one spatial cell (beyond: the path declines)
-constexpr int kCWarps = 8;                   // contraction warps
-constexpr int kGWarps = 4;                   // geometry warps
+#ifndef OB200_CL_CWARPS
+#define OB200_CL_CWARPS 8
+#endif
+#ifndef OB200_CL_GWARPS
+#define OB200_CL_GWARPS 4
+#endif
+#ifndef OB200_CL_RECSLOTS
+#define OB200_CL_RECSLOTS 16
+#endif
+#ifndef OB200_CL_HSLOTS
+#define OB200_CL_HSLOTS 6
+#endif
+constexpr int kCWarps = OB200_CL_CWARPS;     // contraction warps
+constexpr int kGWarps = OB200_CL_GWARPS;     // geometry warps
 constexpr int kClThreads = ( kCWarps + 1 + kGWarps ) * 32;
-constexpr int kSlots = 6;                    // ring of packets (4 elements each)
-constexpr int kHStride = 200;                // doubles per element in the H area: [kstep][3a+i][gp & 3], kstep stride 100
+constexpr int kRecSlots = OB200_CL_RECSLOTS;                // ring of record packets (4 elements each): deep enough to cover the HBM latency
+constexpr int kHSlots = OB200_CL_HSLOTS;                   // ring of gradient packets between the geometry and the contraction warps
+constexpr int kHStride = 200;                // doubles per element in the gradient ring: H[kstep][3a'+i][gp & 3], kstep stride 100
+constexpr int kBankCap = 120;                // positions per shared-memory bank residue (16 residues of 8-byte words)
+constexpr int kPlane = 16 * kBankCap;        // plane stride: positions are handed out per bank residue (see cl_records_kernel)
+static_assert( kCWarps <= 16, "dependency bytes per record" );
 constexpr int kBuildThreads = 128;
 
 struct ClRecord {                            // one (cluster, element) incidence
-    double xyz[24];                          // vertex coordinates
-    unsigned char bidx[64];                  // [a][b]: index of node b's block in the block list of node a (0xFF none)
-    unsigned short nodebase[8];              // first position of node a's blocks in the planes (0xFFFF: not a cluster node)
-    unsigned long long first;                // bit 8a+b: this element is the first of the step to touch block (a,b)
-    unsigned char need[kCWarps];             // elements contraction warp w must have completed in this step before this one
+    double xyz[24];                          // vertex coordinates (the element's own node order)
+    unsigned short pos[64];                  // [a'][b']: position of block (node at row slot a', node at slot b') in the planes,
+                                             // bit 15: this element is the first of the step to touch it; 0xFFFF: no such block here
+    unsigned char need[16];                  // elements contraction warp w must have completed in this step before this one
     int32_t elem;                            // element number, -1 = padding
-    int32_t pad[3];
+    uint32_t slotof;                         // nibble a: row slot a' of the element's node a -- cluster nodes first, so that the
+                                             // lanes with something to add are the first ones of a warp
+    int32_t pad[2];
 };
-static_assert( sizeof( ClRecord ) == 304, "record layout" );
+static_assert( sizeof( ClRecord ) == 352, "record layout" );
 constexpr int kPacketBytes = 4 * (int) sizeof( ClRecord );
 
 struct ClStep {                              // elements of one material of one cluster
@@ -72,15 +89,17 @@ struct ClStep {                              // elements of one material of one 
     int32_t nblocks, nsteps;                 // positions per plane in use; steps of this cluster (valid in its first step)
 };
 // What the flush of a step needs, contiguous in HBM so that one bulk copy brings it into shared memory:
-// the header, per cluster node the start of its (up to 3) rows in val (-1: prescribed dof), per position the column
-// offset of the block in its row | free-dof mask of the column node << 8 | cluster-local node << 16.
+// the header, per cluster node the start of its (up to 3) rows in val (-1: prescribed dof), per block (in row order: node
+// after node, column block after column block) its position in the planes | column offset of the block in its row << 11 |
+// free-dof mask of the column node << 19 | cluster-local node << 22.
 struct ClBlob {
     ClStep hdr;
+    double lam, mu;                          // Lame constants of the step's material
     int32_t rowbase[kClNodes][4];
     uint32_t postab[kClBlocks];
 };
 static_assert( sizeof( ClBlob ) % 16 == 0, "blob layout" );
-constexpr int kBlobHead = (int)( sizeof( ClStep ) + sizeof( int32_t ) * kClNodes * 4 );
+constexpr int kBlobHead = (int)( sizeof( ClStep ) + 2 * sizeof( double ) + sizeof( int32_t ) * kClNodes * 4 );
 
 // ---- spatial cells -> clusters ---------------------------------------------------------------------
 
@@ -157,11 +176,17 @@ struct ClGrid {
 };
 
 __global__ void cl_cell_kernel(const double *__restrict__ coords, const unsigned char *__restrict__ nblk, int64_t nnode, ClGrid g,
-                               int32_t *__restrict__ cell, int32_t *__restrict__ count)
+                               int32_t *__restrict__ cell, int32_t *__restrict__ count, unsigned char *__restrict__ npar)
 {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for ( int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < nnode; n += stride ) {
         int c = -1;
+        {   // parities of the node's position on the grid of element size: bit 2 x, bit 1 y, bit 0 z (bank labels, see below)
+            int pr = 0;
+#pragma unroll
+            for ( int d = 0; d < 3; d++ ) pr = ( pr << 1 ) | ( (int) floor(( coords[n * 3 + d] - g.x0[d] ) * ( 4.0 * g.inv )) & 1 );
+            npar[n] = (unsigned char) pr;
+        }
         if ( nblk[n] ) {
             int k[3];
 #pragma unroll
@@ -231,8 +256,9 @@ struct ClBuildShared {
     unsigned char oloc[kClVisits][8];        // cluster-local index of the element's node a, 0xFF if not a cluster node
     unsigned short outidx[kClVisits];        // position of sorted entry i in the cluster's record range
     short slot2ent[kClVisits + 4 * 64];      // record slot -> sorted entry, -1 = padding
-    int minord[kClBlocks];                   // per position: first record of the step touching it
-    unsigned char need[kClVisits + 4 * 64][kCWarps];
+    int minord[kClBlocks];                   // per block: first record of the step touching it
+    int bpos[kClBlocks];                     // per block (node's first block + index in the node's block list): its position
+    int bankcnt[16];
     unsigned char last[kClNodes][kCWarps];
     unsigned int colormask[kClNodes];
     int32_t nodes[kClNodes];
@@ -268,7 +294,8 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                   int32_t *__restrict__ rec_count, int32_t *__restrict__ step_count,
                   const int32_t *__restrict__ rec_off, const int32_t *__restrict__ step_off,
                   ClRecord *__restrict__ recs, ClBlob *__restrict__ blobs, int *__restrict__ flags,
-                  const int32_t *__restrict__ nodeeq, const int32_t *__restrict__ rowptr, const unsigned short *__restrict__ blk, int maxblk)
+                  const int32_t *__restrict__ nodeeq, const int32_t *__restrict__ rowptr, const unsigned short *__restrict__ blk, int maxblk,
+                  const MatParams *__restrict__ mat, const unsigned char *__restrict__ npar)
 {
     __shared__ ClBuildShared sh;
     const int tid = threadIdx.x;
@@ -398,9 +425,41 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
         __syncthreads();
         for ( int t = tid; t < ne; t += kBuildThreads ) sh.slot2ent[sh.outidx[t]] = (short) t;
         __syncthreads();
+        // Positions in the planes.  The contraction lanes of a half-warp add to the blocks (row node A, column node B) of four
+        // row nodes x four column nodes of one element at a time; the position decides the shared-memory bank.  With
+        // position = bank + 16 k and bank = 4 alpha(A) + beta(B), alpha = the antipodal class of A's grid parities (distinct on
+        // every face of a brick), beta = (z, x) parities of B (distinct on the column sets the slot order below produces), the
+        // sixteen lanes hit sixteen banks on a structured mesh (simulated: 1.08 wavefronts per access instead of 2.1 with
+        // node-contiguous positions); on an unstructured mesh the labels are merely a hash.  First toucher allocates.
+        for ( int t = tid; t < sh.nblocks; t += kBuildThreads ) sh.bpos[t] = -1;
+        if ( tid < 16 ) sh.bankcnt[tid] = 0;
+        __syncthreads();
+        for ( int t = tid; t < ne * 8; t += kBuildThreads ) {
+            const int ei = t >> 3, a = t & 7, la = sh.oloc[ei][a];
+            if ( la == 0xFF ) continue;
+            const int e = sh.elem[ei], nodeA = sh.nodes[la], base = nbase[nodeA];
+            const int pa = npar[nodeA], xa = ( pa >> 2 ) & 1;
+            const int alpha = 2 * ( ( ( pa >> 1 ) & 1 ) ^ xa ) + ( ( pa & 1 ) ^ xa );
+            const unsigned char *bx = ebidx + ( (int64_t) e * 8 + a ) * 8;
+            for ( int b = 0; b < 8; b++ ) {
+                if ( bx[b] == 0xFF ) continue;
+                const int bid = base + bx[b];
+                if ( atomicCAS(&sh.bpos[bid], -1, -2) != -1 ) continue;
+                const int pb = npar[conn[(int64_t) e * 8 + b] - 1];
+                int bank = ( 4 * alpha + 2 * ( pb & 1 ) + ( ( pb >> 2 ) & 1 ) ) & 15, k = 0;
+                for ( int tries = 0; tries < 16; tries++ ) {
+                    k = atomicAdd(&sh.bankcnt[bank], 1);
+                    if ( k < kBankCap ) break;
+                    atomicSub(&sh.bankcnt[bank], 1);
+                    bank = ( bank + 1 ) & 15;
+                }
+                sh.bpos[bid] = bank + 16 * k;          // nblocks <= kClBlocks < 16 kBankCap: some bank has room
+            }
+        }
+        __syncthreads();
         for ( int st = 0; st < nsteps; st++ ) {
             const int s0 = sh.stepinfo[st][0], sn = sh.stepinfo[st][1];
-            // first touch of every position in this step
+            // first touch of every block in this step
             for ( int t = tid; t < sh.nblocks; t += kBuildThreads ) sh.minord[t] = INT_MAX;
             if ( tid < kClNodes * kCWarps ) ( &sh.last[0][0] )[tid] = 0;
             for ( int t = tid + kBuildThreads; t < kClNodes * kCWarps; t += kBuildThreads ) ( &sh.last[0][0] )[t] = 0;
@@ -432,7 +491,7 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                         }
                         if ( tid == r % kCWarps ) nd = 0;          // program order
                     }
-                    sh.need[s0 + r][tid] = (unsigned char) nd;
+                    recs[rec_off[cl] + s0 + r].need[tid] = (unsigned char) nd;
                     __syncwarp(( 1u << kCWarps ) - 1u);
                     if ( ent >= 0 && tid == r % kCWarps ) {
                         const int ei = (int)( sh.key[ent] & 0xFFFF );
@@ -454,41 +513,67 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                 if ( ent < 0 ) {
                     if ( part == 0 ) {
                         R.elem = -1;
-                        R.first = 0;
+                        R.slotof = 0x76543210u;
 #pragma unroll
-                        for ( int w = 0; w < kCWarps; w++ ) R.need[w] = 0;
-#pragma unroll
-                        for ( int a = 0; a < 8; a++ ) R.nodebase[a] = 0xFFFF;
+                        for ( int w = kCWarps; w < 16; w++ ) R.need[w] = 0;
                     }
+#pragma unroll
+                    for ( int q = 0; q < 16; q++ ) R.pos[16 * part + q] = 0xFFFF;
                     continue;
                 }
                 const int ei = (int)( sh.key[ent] & 0xFFFF );
                 const int e = sh.elem[ei];
-                // part p: nodes 2p, 2p+1
-                unsigned long long fbits = 0;
+                // row slots: the element's cluster nodes first, the others behind; inside each group nodes whose x and y
+                // grid parities agree take the even places (as far as there are any): the column sets {0,2,4,6} and
+                // {1,3,5,7} of the contraction lanes then hold nodes with distinct (z, x) parities
+                int slotof[8], nodeat[8];
+                {
+                    unsigned int own = 0, dl = 0;
 #pragma unroll
-                for ( int aa = 0; aa < 2; aa++ ) {
-                    const int a = 2 * part + aa;
-                    const int node = conn[(int64_t) e * 8 + a] - 1;
+                    for ( int a = 0; a < 8; a++ ) {
+                        if ( sh.oloc[ei][a] != 0xFF ) own |= 1u << a;
+                        const int pr = npar[conn[(int64_t) e * 8 + a] - 1];
+                        if ( ( ( pr >> 2 ) ^ ( pr >> 1 ) ) & 1 ) dl |= 1u << a;
+                    }
+                    int k = 0;
 #pragma unroll
-                    for ( int d = 0; d < 3; d++ ) R.xyz[3 * a + d] = coords[(int64_t) node * 3 + d];
-                    const int la = sh.oloc[ei][a];
-                    const int base = la != 0xFF ? (int) nbase[node] : 0xFFFF;
-                    R.nodebase[a] = (unsigned short) base;
-                    const unsigned char *bx = ebidx + ( (int64_t) e * 8 + a ) * 8;
-#pragma unroll
-                    for ( int b = 0; b < 8; b++ ) {
-                        const unsigned char bi = bx[b];
-                        R.bidx[a * 8 + b] = bi;
-                        if ( la != 0xFF && bi != 0xFF && sh.minord[base + bi] == r ) fbits |= 1ull << ( 8 * a + b );
+                    for ( int grp = 0; grp < 2; grp++ ) {
+                        const unsigned int in = grp == 0 ? own : ( ~own & 0xFFu );
+                        unsigned int me = in & ~dl, mo = in & dl;
+                        while ( me | mo ) {
+                            if ( me ) { const int a = __ffs(me) - 1; slotof[a] = k; nodeat[k] = a; k++; me &= me - 1; }
+                            if ( mo ) { const int a = __ffs(mo) - 1; slotof[a] = k; nodeat[k] = a; k++; mo &= mo - 1; }
+                        }
                     }
                 }
-                // part p owns bits 16p .. 16p+15 of the first-touch word
-                reinterpret_cast< unsigned short * >( &R.first )[part] = (unsigned short)( fbits >> ( 16 * part ) );
+                // part p: slots 2p, 2p+1 (and the coordinates of nodes 2p, 2p+1, which stay in the element's own order)
+#pragma unroll
+                for ( int aa = 0; aa < 2; aa++ ) {
+                    const int a0 = 2 * part + aa;
+                    const int node0 = conn[(int64_t) e * 8 + a0] - 1;
+#pragma unroll
+                    for ( int d = 0; d < 3; d++ ) R.xyz[3 * a0 + d] = coords[(int64_t) node0 * 3 + d];
+                    const int sl = 2 * part + aa;
+                    const int a = nodeat[sl];
+                    const int node = conn[(int64_t) e * 8 + a] - 1;
+                    const int la = sh.oloc[ei][a];
+                    const int base = la != 0xFF ? (int) nbase[node] : 0;
+                    const unsigned char *bx = ebidx + ( (int64_t) e * 8 + a ) * 8;
+                    for ( int b = 0; b < 8; b++ ) {
+                        const unsigned char bi = bx[b];
+                        unsigned short pv = 0xFFFF;
+                        if ( la != 0xFF && bi != 0xFF ) pv = (unsigned short)( sh.bpos[base + bi] | ( sh.minord[base + bi] == r ? 0x8000 : 0 ) );
+                        R.pos[sl * 8 + slotof[b]] = pv;
+                    }
+                }
                 if ( part == 0 ) {
                     R.elem = e;
+                    uint32_t w = 0;
 #pragma unroll
-                    for ( int w = 0; w < kCWarps; w++ ) R.need[w] = sh.need[s0 + r][w];
+                    for ( int a = 0; a < 8; a++ ) w |= (uint32_t) slotof[a] << ( 4 * a );
+                    R.slotof = w;
+#pragma unroll
+                    for ( int w2 = kCWarps; w2 < 16; w2++ ) R.need[w2] = 0;
                 }
             }
             // the flush tables of the step
@@ -503,6 +588,8 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                 S.flags = ( st > 0 ? 1 : 0 ) | ( nsteps > 1 ? 2 : 0 ) | ( st == nsteps - 1 ? 4 : 0 );
                 S.nblocks = sh.nblocks;
                 S.nsteps = nsteps;
+                const MatParams &mp = mat[sh.stepinfo[st][2]];
+                isole_lame(mp.E, mp.nu, B.lam, B.mu);
             }
             for ( int k = tid; k < nn; k += kBuildThreads ) {
                 const int w = sh.nodes[k], nb = nblk[w], base = nbase[w];
@@ -515,7 +602,7 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                 int cstart = 0;
                 for ( int n = 0; n < nb; n++ ) {
                     const int cm = blk[(int64_t) w * maxblk + n] >> 8;
-                    B.postab[base + n] = (uint32_t) cstart | ( (uint32_t) cm << 8 ) | ( (uint32_t) k << 16 );
+                    B.postab[base + n] = (uint32_t) sh.bpos[base + n] | ( (uint32_t) cstart << 11 ) | ( (uint32_t) cm << 19 ) | ( (uint32_t) k << 22 );
                     cstart += __popc(cm);
                 }
             }
@@ -526,15 +613,12 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
 
 // ---- the assembly kernel --------------------------------------------------------------------------------
 
-struct ClSlot {
-    ClRecord rec[4];
-    double H[4][kHStride];
-};
 struct ClShared {
-    double acc[9 * kClBlocks];
-    ClSlot slot[kSlots];
+    double acc[9 * kPlane];
+    double H[kHSlots][4][kHStride];
+    ClRecord rec[kRecSlots][4];
     ClBlob blob[2];
-    unsigned long long full_p[kSlots], full_g[kSlots], empty[kSlots], blob_full[2], blob_empty[2];
+    unsigned long long full_p[kRecSlots], empty_r[kRecSlots], full_g[kHSlots], empty_h[kHSlots], blob_full[2], blob_empty[2];
     volatile unsigned int done[kCWarps];
 };
 
@@ -578,7 +662,7 @@ __device__ __forceinline__ void cl_dmma(double &c0, double &c1, double a, double
 // J = x dN/dxi, dN/dx = dN/dxi J^-1 (evaldNdx, fei3dhexalin.C:186-204); dV = |det J|
 // (Structural3DElement::computeVolumeAround, structural3delement.C:328-338).  J^-1 sqrt|det J| = adj(J) sign(det) / sqrt|det|:
 // one reciprocal square root instead of a division and a square root.
-__device__ __forceinline__ void cl_geometry(const double *__restrict__ xv, int gp, double *__restrict__ Hel)
+__device__ __forceinline__ void cl_geometry(const double *__restrict__ xv, int gp, uint32_t slotof, double *__restrict__ Hel)
 {
     constexpr double kA = 0.577350269189626;
     constexpr double pp = 0.125 * ( 1.0 + kA ) * ( 1.0 + kA ), pm = 0.125 * ( 1.0 + kA ) * ( 1.0 - kA ), mm = 0.125 * ( 1.0 - kA ) * ( 1.0 - kA );
@@ -636,9 +720,11 @@ __device__ __forceinline__ void cl_geometry(const double *__restrict__ xv, int g
         for ( int j = 0; j < 3; j++ ) A[i][j] *= s;
     double *o = Hel + ( gp >> 2 ) * 100 + ( gp & 3 );
 #pragma unroll
-    for ( int kk = 0; kk < 8; kk++ )
+    for ( int kk = 0; kk < 8; kk++ ) {
+        double *ok = o + 12 * ( ( slotof >> ( 4 * kk ) ) & 7u );          // row slot of node kk
 #pragma unroll
-        for ( int j = 0; j < 3; j++ ) o[4 * ( 3 * kk + j )] = dN[kk][0] * A[0][j] + dN[kk][1] * A[1][j] + dN[kk][2] * A[2][j];
+        for ( int j = 0; j < 3; j++ ) ok[4 * j] = dN[kk][0] * A[0][j] + dN[kk][1] * A[1][j] + dN[kk][2] * A[2][j];
+    }
 }
 
 struct ClView {
@@ -685,10 +771,13 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
     ClShared &sh = *reinterpret_cast< ClShared * >( cl_smem_raw );
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if ( tid == 0 ) {
-        for ( int s = 0; s < kSlots; s++ ) {
+        for ( int s = 0; s < kRecSlots; s++ ) {
             cl_mbar_init(&sh.full_p[s], 1);
+            cl_mbar_init(&sh.empty_r[s], 4);
+        }
+        for ( int s = 0; s < kHSlots; s++ ) {
             cl_mbar_init(&sh.full_g[s], 1);
-            cl_mbar_init(&sh.empty[s], 4);
+            cl_mbar_init(&sh.empty_h[s], 4);
         }
         for ( int b = 0; b < 2; b++ ) {
             cl_mbar_init(&sh.blob_full[b], 1);
@@ -712,11 +801,11 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             cl_mbar_expect_tx(&sh.blob_full[b], bytes);
             cl_bulk_load(&sh.blob[b], blob, bytes, &sh.blob_full[b]);
             for ( int k = 0; k < npk; k++, pseq++ ) {
-                const int s = pseq % kSlots;
-                const unsigned int round = pseq / kSlots;
-                if ( round > 0 ) cl_mbar_wait(&sh.empty[s], ( round - 1 ) & 1);
+                const int s = pseq % kRecSlots;
+                const unsigned int round = pseq / kRecSlots;
+                if ( round > 0 ) cl_mbar_wait(&sh.empty_r[s], ( round - 1 ) & 1);
                 cl_mbar_expect_tx(&sh.full_p[s], kPacketBytes);
-                cl_bulk_load(sh.slot[s].rec, V.recs + rec_begin + 4 * k, kPacketBytes, &sh.full_p[s]);
+                cl_bulk_load(sh.rec[s], V.recs + rec_begin + 4 * k, kPacketBytes, &sh.full_p[s]);
             }
         }
         return;
@@ -730,12 +819,13 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             const int npk = V.blobs[w.st].hdr.npk;
             for ( int k = 0; k < npk; k++, pseq++ ) {
                 if ( (int)( pseq % kGWarps ) != g ) continue;
-                const int s = pseq % kSlots;
-                cl_mbar_wait(&sh.full_p[s], ( pseq / kSlots ) & 1);
-                const ClRecord &R = sh.slot[s].rec[lane >> 3];
-                if ( R.elem >= 0 ) cl_geometry(R.xyz, lane & 7, sh.slot[s].H[lane >> 3]);
+                const int rs = pseq % kRecSlots, hs = pseq % kHSlots;
+                cl_mbar_wait(&sh.full_p[rs], ( pseq / kRecSlots ) & 1);
+                if ( pseq >= kHSlots ) cl_mbar_wait(&sh.empty_h[hs], ( pseq / kHSlots - 1 ) & 1);
+                const ClRecord &R = sh.rec[rs][lane >> 3];
+                if ( R.elem >= 0 ) cl_geometry(R.xyz, lane & 7, R.slotof, sh.H[hs][lane >> 3]);
                 __syncwarp();
-                if ( lane == 0 ) cl_mbar_arrive(&sh.full_g[s]);
+                if ( lane == 0 ) cl_mbar_arrive(&sh.full_g[hs]);
             }
         }
         return;
@@ -755,19 +845,19 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             const ClStep step = blob.hdr;
             last = ( step.flags & 4 ) != 0;
             if ( step.flags & 2 ) {         // several materials in this cluster: positions a step does not touch must read as zero
-                for ( int t = tid; t < 9 * kClBlocks; t += kCWarps * 32 ) sh.acc[t] = 0.0;
+                for ( int t = tid; t < 9 * kPlane; t += kCWarps * 32 ) sh.acc[t] = 0.0;
                 asm volatile( "bar.sync 1, %0;" ::"n"( kCWarps * 32 ) : "memory" );
             }
             const int nrec = step.npk * 4;
             unsigned int mydone = 0;
             for ( int r = wid; r < nrec; r += kCWarps ) {
                 const unsigned int pseq = pseq0 + ( r >> 2 );
-                const int s = pseq % kSlots;
-                cl_mbar_wait(&sh.full_p[s], ( pseq / kSlots ) & 1);      // the records (bulk copy)
-                cl_mbar_wait(&sh.full_g[s], ( pseq / kSlots ) & 1);      // the gradients (geometry warp)
-                const ClRecord &R = sh.slot[s].rec[r & 3];
+                const int rs = pseq % kRecSlots, hs = pseq % kHSlots;
+                cl_mbar_wait(&sh.full_p[rs], ( pseq / kRecSlots ) & 1);      // the records (bulk copy)
+                cl_mbar_wait(&sh.full_g[hs], ( pseq / kHSlots ) & 1);        // the gradients (geometry warp)
+                const ClRecord &R = sh.rec[rs][r & 3];
                 if ( R.elem >= 0 ) {
-                    const double *H = sh.slot[s].H[r & 3] + 12 * a + bp;
+                    const double *H = sh.H[hs][r & 3] + 12 * a + bp;
                     // fragments: h[i][ks] = H[ks][3a+i][bp] -- both the A fragment of component i and the B fragment of component i
                     double h[3][2];
 #pragma unroll
@@ -775,14 +865,11 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                         h[i][0] = H[4 * i];
                         h[i][1] = H[100 + 4 * i];
                     }
-                    const unsigned int nb_a = R.nodebase[a];
-                    const unsigned int nbb = *reinterpret_cast< const unsigned int * >( &R.nodebase[b0] );
-                    const unsigned int bx = *reinterpret_cast< const unsigned short * >( &R.bidx[a * 8 + b0] );
-                    const unsigned int t0 = R.bidx[b0 * 8 + a], t1 = R.bidx[b1 * 8 + a];
-                    const unsigned long long first = R.first;
+                    // row slot a of this lane, column slots b0, b1
+                    const unsigned int pp = *reinterpret_cast< const unsigned int * >( &R.pos[a * 8 + b0] );
                     const unsigned int nd = lane < kCWarps ? R.need[lane] : 0u;
                     // the six products (accumulators start at zero; two k-steps of four Gauss points)
-                    double d[6][2];
+                    double d[9][2];
 #pragma unroll
                     for ( int t = 0; t < 6; t++ ) d[t][0] = d[t][1] = 0.0;
 #pragma unroll
@@ -794,42 +881,44 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                         cl_dmma(d[4][0], d[4][1], h[0][ks], h[2][ks]);     // (0,2)
                         cl_dmma(d[5][0], d[5][1], h[1][ks], h[2][ks]);     // (1,2)
                     }
-                    // where the entries go: P = block (a, b) of this lane's two columns, Q = the transposed blocks (b, a)
-                    const bool vp0 = nb_a != 0xFFFFu && ( bx & 0xFFu ) != 0xFFu, vp1 = nb_a != 0xFFFFu && ( bx >> 8 ) != 0xFFu;
-                    const bool vq0 = ( nbb & 0xFFFFu ) != 0xFFFFu && t0 != 0xFFu, vq1 = ( nbb >> 16 ) != 0xFFFFu && t1 != 0xFFu;
-                    // a first touch overwrites: the old value is then not read at all
-                    const bool lp0 = vp0 && !( ( first >> ( 8 * a + b0 ) ) & 1 ), lp1 = vp1 && !( ( first >> ( 8 * a + b1 ) ) & 1 );
-                    const bool lq0 = vq0 && !( ( first >> ( 8 * b0 + a ) ) & 1 ), lq1 = vq1 && !( ( first >> ( 8 * b1 + a ) ) & 1 );
-                    double *const p0 = sh.acc + ( vp0 ? nb_a + ( bx & 0xFFu ) : 0u ), *const p1 = sh.acc + ( vp1 ? nb_a + ( bx >> 8 ) : 0u );
-                    double *const q0 = sh.acc + ( vq0 ? ( nbb & 0xFFFFu ) + t0 : 0u ), *const q1 = sh.acc + ( vq1 ? ( nbb >> 16 ) + t1 : 0u );
+                    // tiles (1,0), (2,0), (2,1) are the transposes of (0,1), (0,2), (1,2) over the node pairs: three 64-bit
+                    // shuffles per tile (swap inside the 2x2 blocks a lane pair holds, then exchange the blocks)
+                    {
+                        const bool odd = ( lane & 4 ) != 0;
+                        const int src = ( ( ( lane & 3 ) * 2 + ( ( lane >> 2 ) & 1 ) ) << 2 ) + ( lane >> 3 );
+#pragma unroll
+                        for ( int t = 0; t < 3; t++ ) {
+                            double v0 = d[3 + t][0], v1 = d[3 + t][1];
+                            const double recv = __shfl_xor_sync(0xffffffffu, odd ? v0 : v1, 4);
+                            if ( odd ) v0 = recv; else v1 = recv;
+                            d[6 + t][0] = __shfl_sync(0xffffffffu, v0, src);
+                            d[6 + t][1] = __shfl_sync(0xffffffffu, v1, src);
+                        }
+                    }
+                    const bool v0 = ( pp & 0xFFFFu ) != 0xFFFFu, v1 = ( pp >> 16 ) != 0xFFFFu;
+                    // a first touch overwrites: the old value is then not read
+                    const bool l0 = v0 && !( pp & 0x8000u ), l1 = v1 && !( pp & 0x80000000u );
+                    double *const p0 = sh.acc + ( pp & 0x7FFFu ), *const p1 = sh.acc + ( ( pp >> 16 ) & 0x7FFFu );
                     // wait until every earlier element sharing a cluster node with this one has been added
                     if ( nd )
                         while ( sh.done[lane] < nd ) { }
                     __syncwarp();
                     __threadfence_block();
-                    // planes: (0,0) -> 0, (1,1) -> 4, (2,2) -> 8, (0,1) -> 1 | 3, (0,2) -> 2 | 6, (1,2) -> 5 | 7.
-                    // All loads first, then the additions, then the stores: the positions of one lane are distinct.
-                    constexpr int kPl[6] = { 0, 4, 8, 1, 2, 5 }, kPlT[3] = { 3, 6, 7 };
-                    double op[6][2], oq[3][2];
+                    // planes 3i+j: (0,0) (1,1) (2,2) (0,1) (0,2) (1,2) (1,0) (2,0) (2,1).  All loads first, then the additions,
+                    // then the stores: the positions of one lane are distinct.
+                    constexpr int kPl[9] = { 0, 4, 8, 1, 2, 5, 3, 6, 7 };
+                    double o0[9], o1[9];
 #pragma unroll
-                    for ( int t = 0; t < 6; t++ ) {
-                        op[t][0] = lp0 ? p0[kPl[t] * kClBlocks] : 0.0;
-                        op[t][1] = lp1 ? p1[kPl[t] * kClBlocks] : 0.0;
+                    for ( int t = 0; t < 9; t++ ) {
+                        o0[t] = 0.0;
+                        o1[t] = 0.0;
+                        if ( l0 ) o0[t] = p0[kPl[t] * kPlane];
+                        if ( l1 ) o1[t] = p1[kPl[t] * kPlane];
                     }
 #pragma unroll
-                    for ( int t = 0; t < 3; t++ ) {
-                        oq[t][0] = lq0 ? q0[kPlT[t] * kClBlocks] : 0.0;
-                        oq[t][1] = lq1 ? q1[kPlT[t] * kClBlocks] : 0.0;
-                    }
-#pragma unroll
-                    for ( int t = 0; t < 6; t++ ) {
-                        if ( vp0 ) p0[kPl[t] * kClBlocks] = op[t][0] + d[t][0];
-                        if ( vp1 ) p1[kPl[t] * kClBlocks] = op[t][1] + d[t][1];
-                    }
-#pragma unroll
-                    for ( int t = 0; t < 3; t++ ) {
-                        if ( vq0 ) q0[kPlT[t] * kClBlocks] = oq[t][0] + d[3 + t][0];
-                        if ( vq1 ) q1[kPlT[t] * kClBlocks] = oq[t][1] + d[3 + t][1];
+                    for ( int t = 0; t < 9; t++ ) {
+                        if ( v0 ) p0[kPl[t] * kPlane] = o0[t] + d[t][0];
+                        if ( v1 ) p1[kPl[t] * kPlane] = o1[t] + d[t][1];
                     }
                 }
                 mydone++;
@@ -837,24 +926,23 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                 if ( lane == 0 ) {
                     __threadfence_block();
                     sh.done[wid] = mydone;
-                    cl_mbar_arrive(&sh.empty[s]);
+                    cl_mbar_arrive(&sh.empty_r[rs]);
+                    cl_mbar_arrive(&sh.empty_h[hs]);
                 }
             }
             pseq0 += step.npk;
             asm volatile( "bar.sync 1, %0;" ::"n"( kCWarps * 32 ) : "memory" );
 
-            // ---- flush: one thread per position (3x3 block); consecutive positions are consecutive column blocks of a node ----
-            const MatParams *mp = S.mat + step.matid;
-            double lam, mu;
-            isole_lame(mp->E, mp->nu, lam, mu);
+            // ---- flush: one thread per 3x3 block, in row order (consecutive threads write consecutive column blocks of a node) ----
+            const double lam = blob.lam, mu = blob.mu;
             const bool add = ACCUM || ( step.flags & 1 );
-            for ( int p = tid; p < step.nblocks; p += kCWarps * 32 ) {
-                const uint32_t info = blob.postab[p];
-                const int cstart = info & 0xFF, cm = ( info >> 8 ) & 7;
-                const int4 rb = *reinterpret_cast< const int4 * >( blob.rowbase[info >> 16] );
+            for ( int q = tid; q < step.nblocks; q += kCWarps * 32 ) {
+                const uint32_t info = blob.postab[q];
+                const int p = info & 0x7FF, cstart = ( info >> 11 ) & 0xFF, cm = ( info >> 19 ) & 7;
+                const int4 rb = *reinterpret_cast< const int4 * >( blob.rowbase[info >> 22] );
                 double g[9];
 #pragma unroll
-                for ( int c = 0; c < 9; c++ ) g[c] = sh.acc[c * kClBlocks + p];
+                for ( int c = 0; c < 9; c++ ) g[c] = sh.acc[c * kPlane + p];
                 const double tr = mu * ( g[0] + g[4] + g[8] );
                 double kb[9];
                 kb[0] = lam * g[0] + mu * g[0] + tr; kb[1] = lam * g[1] + mu * g[3];      kb[2] = lam * g[2] + mu * g[6];
@@ -946,7 +1034,8 @@ int cluster_bind(ob200_elemset *S, ob200_csr *A)
     OB_CHECK( s64.alloc(ncell + 1) );
     OB_CUDA( cudaMemsetAsync(ccount.p, 0, sizeof( int32_t ) * ( ncell + 1 ), ctx->stream) );
     OB_CUDA( cudaMemsetAsync(cfill.p, 0, sizeof( int32_t ) * ( ncell + 1 ), ctx->stream) );
-    OB_LAUNCH(ctx, cl_cell_kernel, ctx->shape.grid(nnode, 256, 4), 256, 0, S->coords.p, S->nblk.p, nnode, g, cell.p, ccount.p);
+    OB_CHECK( S->npar.alloc(nnode) );
+    OB_LAUNCH(ctx, cl_cell_kernel, ctx->shape.grid(nnode, 256, 4), 256, 0, S->coords.p, S->nblk.p, nnode, g, cell.p, ccount.p, S->npar.p);
     int32_t maxcell = 0;
     OB_CHECK( max_reduce(ctx, ccount.p, ncell, &maxcell) );
     if ( maxcell > kClMaxCell ) return OB200_OK;
@@ -988,7 +1077,7 @@ int cluster_bind(ob200_elemset *S, ob200_csr *A)
     OB_LAUNCH(ctx, cl_records_kernel< false >, bgrid, kBuildThreads, 0, (int32_t) nclusters, S->cl_begin.p, S->cnodes.p, S->ninc_start.p,
               S->ninc.p, S->conn.p, S->coords.p, S->matid.p, S->ncl.p, S->nbase.p, S->nloc.p, S->nblk.p, S->ebidx.p, rcount.p, scount.p,
               (const int32_t *) nullptr, (const int32_t *) nullptr, (ClRecord *) nullptr, (ClBlob *) nullptr, flags.p,
-              S->nodeeq.p, A->rowptr.p, S->blk.p, S->maxblk);
+              S->nodeeq.p, A->rowptr.p, S->blk.p, S->maxblk, (const MatParams *) S->mat.p, S->npar.p);
     int64_t nrec = 0, nsteps = 0;
     DevBuf< int64_t > c64;
     OB_CHECK( c64.alloc(nclusters + 1) );
@@ -1005,7 +1094,7 @@ int cluster_bind(ob200_elemset *S, ob200_csr *A)
     OB_LAUNCH(ctx, cl_records_kernel< true >, bgrid, kBuildThreads, 0, (int32_t) nclusters, S->cl_begin.p, S->cnodes.p, S->ninc_start.p,
               S->ninc.p, S->conn.p, S->coords.p, S->matid.p, S->ncl.p, S->nbase.p, S->nloc.p, S->nblk.p, S->ebidx.p, rcount.p, scount.p,
               roff.p, S->cl_step.p, (ClRecord *) S->cl_recs.p, (ClBlob *) S->cl_steps.p, flags.p,
-              S->nodeeq.p, A->rowptr.p, S->blk.p, S->maxblk);
+              S->nodeeq.p, A->rowptr.p, S->blk.p, S->maxblk, (const MatParams *) S->mat.p, S->npar.p);
     OB_CUDA( cudaMemcpyAsync(&hflag, flags.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
     if ( hflag ) return OB200_OK;

@@ -78,7 +78,7 @@ struct ob200_elemset {
     bool cluster_ok = false;
     int32_t nclusters = 0;
     int64_t cl_nrec = 0;
-    ob200::DevBuf< unsigned char > ebidx, nloc, cl_recs, cl_steps;
+    ob200::DevBuf< unsigned char > ebidx, nloc, npar, cl_recs, cl_steps;
     ob200::DevBuf< unsigned short > nbase;
     ob200::DevBuf< int32_t > cnodes, ncl, cl_begin, cl_step;
     bool all_isole = true;

@@ -17,7 +17,7 @@ d = [t(pb["coords"]), t(pb["conn"]), t(np.zeros(nelem, np.int32)), t(pb["loc"])]
 A = CudaCSR(ctx)
 A.buildInternalStructure(d[3], neq)
 vals = {}
-for path in ("cluster", "gather"):
+for path in (("cluster", "gather") if not os.environ.get("OB200_ONLY") else (os.environ["OB200_ONLY"],)):
     if path == "gather":
         os.environ["OB200_ASSEMBLY"] = "gather"
     else:
@@ -35,5 +35,6 @@ for path in ("cluster", "gather"):
     vals[path] = A.values().copy() if isinstance(A.values(), np.ndarray) else A.values()
     print(path, "bind_s %.4f" % tb, {k: (round(v[0] / v[1], 4), v[1]) for k, v in prof.items()})
     S.close()
-a, b = np.asarray(vals["cluster"]), np.asarray(vals["gather"])
-print("relerr cluster vs gather:", float(np.abs(a - b).max() / np.abs(b).max()), "nnz", a.size)
+if len(vals) == 2:
+  a, b = np.asarray(vals["cluster"]), np.asarray(vals["gather"])
+  print("relerr cluster vs gather:", float(np.abs(a - b).max() / np.abs(b).max()), "nnz", a.size)
