@@ -76,7 +76,7 @@ struct ClRecord {                            // one (cluster, element) incidence
     int32_t elem;                            // element number, -1 = padding
     uint32_t slotof;                         // nibble a: row slot a' of the element's node a -- cluster nodes first, so that the
                                              // lanes with something to add are the first ones of a warp
-    int32_t pad[2];
+    int32_t pad[2];                          // pad[0]: number of cluster nodes of the element (the first row slots)
 };
 static_assert( sizeof( ClRecord ) == 352, "record layout" );
 constexpr int kPacketBytes = 4 * (int) sizeof( ClRecord );
@@ -89,9 +89,9 @@ struct ClStep {                              // elements of one material of one 
     int32_t nblocks, nsteps;                 // positions per plane in use; steps of this cluster (valid in its first step)
 };
 // What the flush of a step needs, contiguous in HBM so that one bulk copy brings it into shared memory:
-// the header, per cluster node the start of its (up to 3) rows in val (-1: prescribed dof), per block (in row order: node
-// after node, column block after column block) its position in the planes | column offset of the block in its row << 11 |
-// free-dof mask of the column node << 19 | cluster-local node << 22.
+// the header, per cluster node the start of its (up to 3) rows in val (-1: prescribed dof) and its first block | blocks << 16,
+// per block (A, B) (in row order: node after node, column block after column block) its position in the planes | position of
+// the transposed block (B, A) << 11 | free-dof mask of the column node << 22 | (B is a cluster node) << 25.
 struct ClBlob {
     ClStep hdr;
     double lam, mu;                          // Lame constants of the step's material
@@ -181,10 +181,15 @@ __global__ void cl_cell_kernel(const double *__restrict__ coords, const unsigned
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for ( int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < nnode; n += stride ) {
         int c = -1;
-        {   // parities of the node's position on the grid of element size: bit 2 x, bit 1 y, bit 0 z (bank labels, see below)
+        {   // the node's position on the grid of element size, two bits per axis: bit 2 x, bit 1 y, bit 0 z parities, bits 5..3
+            // the next bit of x, y, z (bank labels, see cl_records_kernel)
             int pr = 0;
 #pragma unroll
-            for ( int d = 0; d < 3; d++ ) pr = ( pr << 1 ) | ( (int) floor(( coords[n * 3 + d] - g.x0[d] ) * ( 4.0 * g.inv )) & 1 );
+            for ( int d = 0; d < 3; d++ ) {
+                const int k = (int) floor(( coords[n * 3 + d] - g.x0[d] ) * ( 4.0 * g.inv ));
+                pr |= ( k & 1 ) << ( 2 - d );
+                pr |= ( ( k >> 1 ) & 1 ) << ( 5 - d );
+            }
             npar[n] = (unsigned char) pr;
         }
         if ( nblk[n] ) {
@@ -257,7 +262,8 @@ struct ClBuildShared {
     unsigned short outidx[kClVisits];        // position of sorted entry i in the cluster's record range
     short slot2ent[kClVisits + 4 * 64];      // record slot -> sorted entry, -1 = padding
     int minord[kClBlocks];                   // per block: first record of the step touching it
-    int bpos[kClBlocks];                     // per block (node's first block + index in the node's block list): its position
+    unsigned short bpos[kClBlocks];          // per block (node's first block + index in the node's block list): its position
+    unsigned short tbid[kClBlocks];          // per block (A, B): the block (B, A) if B is a cluster node, else 0xFFFF
     int bankcnt[16];
     unsigned char last[kClNodes][kCWarps];
     unsigned int colormask[kClNodes];
@@ -427,11 +433,11 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
         __syncthreads();
         // Positions in the planes.  The contraction lanes of a half-warp add to the blocks (row node A, column node B) of four
         // row nodes x four column nodes of one element at a time; the position decides the shared-memory bank.  With
-        // position = bank + 16 k and bank = 4 alpha(A) + beta(B), alpha = the antipodal class of A's grid parities (distinct on
+        // position = bank + 16 k and bank = 4 (alpha(A) + kappa(B)) + beta(B), alpha = the antipodal class of A's grid parities (distinct on
         // every face of a brick), beta = (z, x) parities of B (distinct on the column sets the slot order below produces), the
         // sixteen lanes hit sixteen banks on a structured mesh (simulated: 1.08 wavefronts per access instead of 2.1 with
         // node-contiguous positions); on an unstructured mesh the labels are merely a hash.  First toucher allocates.
-        for ( int t = tid; t < sh.nblocks; t += kBuildThreads ) sh.bpos[t] = -1;
+        for ( int t = tid; t < sh.nblocks; t += kBuildThreads ) { sh.bpos[t] = 0xFFFF; sh.tbid[t] = 0xFFFF; }
         if ( tid < 16 ) sh.bankcnt[tid] = 0;
         __syncthreads();
         for ( int t = tid; t < ne * 8; t += kBuildThreads ) {
@@ -444,16 +450,24 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
             for ( int b = 0; b < 8; b++ ) {
                 if ( bx[b] == 0xFF ) continue;
                 const int bid = base + bx[b];
-                if ( atomicCAS(&sh.bpos[bid], -1, -2) != -1 ) continue;
+                if ( atomicCAS(&sh.bpos[bid], (unsigned short) 0xFFFF, (unsigned short) 0xFFFE) != 0xFFFF ) continue;
+                const int lb = sh.oloc[ei][b];
+                if ( lb != 0xFF ) {           // the transposed block, also accumulated in this cluster
+                    const unsigned char tb = ebidx[( (int64_t) e * 8 + b ) * 8 + a];
+                    if ( tb != 0xFF ) sh.tbid[bid] = (unsigned short)( nbase[sh.nodes[lb]] + tb );
+                }
                 const int pb = npar[conn[(int64_t) e * 8 + b] - 1];
-                int bank = ( 4 * alpha + 2 * ( pb & 1 ) + ( ( pb >> 2 ) & 1 ) ) & 15, k = 0;
+                // kappa(B) (any function of the column node keeps the sixteen lanes apart) spreads the blocks of one row node
+                // over all banks for the flush: y parity and the next bit of y (searched: at most 2 blocks of 16 share a bank)
+                const int kappa = 2 * ( ( pb >> 1 ) & 1 ) + ( ( pb >> 4 ) & 1 );
+                int bank = ( 4 * ( ( alpha + kappa ) & 3 ) + 2 * ( pb & 1 ) + ( ( pb >> 2 ) & 1 ) ) & 15, k = 0;
                 for ( int tries = 0; tries < 16; tries++ ) {
                     k = atomicAdd(&sh.bankcnt[bank], 1);
                     if ( k < kBankCap ) break;
                     atomicSub(&sh.bankcnt[bank], 1);
                     bank = ( bank + 1 ) & 15;
                 }
-                sh.bpos[bid] = bank + 16 * k;          // nblocks <= kClBlocks < 16 kBankCap: some bank has room
+                sh.bpos[bid] = (unsigned short)( bank + 16 * k );          // nblocks <= kClBlocks < 16 kBankCap: some bank has room
             }
         }
         __syncthreads();
@@ -568,6 +582,10 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                 }
                 if ( part == 0 ) {
                     R.elem = e;
+                    int nown = 0;
+#pragma unroll
+                    for ( int a = 0; a < 8; a++ ) nown += sh.oloc[ei][a] != 0xFF;
+                    R.pad[0] = nown;
                     uint32_t w = 0;
 #pragma unroll
                     for ( int a = 0; a < 8; a++ ) w |= (uint32_t) slotof[a] << ( 4 * a );
@@ -598,12 +616,12 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                     const int eq = nodeeq[(int64_t) w * 3 + i];
                     B.rowbase[k][i] = eq > 0 ? rowptr[eq - 1] : -1;
                 }
-                B.rowbase[k][3] = 0;
-                int cstart = 0;
+                B.rowbase[k][3] = base | ( nb << 16 );
                 for ( int n = 0; n < nb; n++ ) {
                     const int cm = blk[(int64_t) w * maxblk + n] >> 8;
-                    B.postab[base + n] = (uint32_t) sh.bpos[base + n] | ( (uint32_t) cstart << 11 ) | ( (uint32_t) cm << 19 ) | ( (uint32_t) k << 22 );
-                    cstart += __popc(cm);
+                    const int tb = sh.tbid[base + n];
+                    B.postab[base + n] = (uint32_t) sh.bpos[base + n] | ( (uint32_t)( tb != 0xFFFF ? sh.bpos[tb] : 0 ) << 11 ) |
+                                         ( (uint32_t) cm << 22 ) | ( tb != 0xFFFF ? 1u << 25 : 0u );
                 }
             }
             __syncthreads();
@@ -866,10 +884,15 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                         h[i][1] = H[100 + 4 * i];
                     }
                     // row slot a of this lane, column slots b0, b1
-                    const unsigned int pp = *reinterpret_cast< const unsigned int * >( &R.pos[a * 8 + b0] );
+                    // lanes whose row node (slot a) belongs to the cluster add to block (a, b); lanes whose row node does not,
+                    // but whose column node does, add the off-diagonal products to the transposed planes of block (b, a) -- for
+                    // pairs inside the cluster the flush reads entry (j,i) of block (a,b) as entry (i,j) of block (b,a) instead
+                    const bool rown = a < R.pad[0];
+                    const unsigned int pp = rown ? *reinterpret_cast< const unsigned int * >( &R.pos[a * 8 + b0] )
+                                                 : (unsigned int) R.pos[b0 * 8 + a] | ( (unsigned int) R.pos[b1 * 8 + a] << 16 );
                     const unsigned int nd = lane < kCWarps ? R.need[lane] : 0u;
                     // the six products (accumulators start at zero; two k-steps of four Gauss points)
-                    double d[9][2];
+                    double d[6][2];
 #pragma unroll
                     for ( int t = 0; t < 6; t++ ) d[t][0] = d[t][1] = 0.0;
 #pragma unroll
@@ -881,44 +904,39 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                         cl_dmma(d[4][0], d[4][1], h[0][ks], h[2][ks]);     // (0,2)
                         cl_dmma(d[5][0], d[5][1], h[1][ks], h[2][ks]);     // (1,2)
                     }
-                    // tiles (1,0), (2,0), (2,1) are the transposes of (0,1), (0,2), (1,2) over the node pairs: three 64-bit
-                    // shuffles per tile (swap inside the 2x2 blocks a lane pair holds, then exchange the blocks)
-                    {
-                        const bool odd = ( lane & 4 ) != 0;
-                        const int src = ( ( ( lane & 3 ) * 2 + ( ( lane >> 2 ) & 1 ) ) << 2 ) + ( lane >> 3 );
-#pragma unroll
-                        for ( int t = 0; t < 3; t++ ) {
-                            double v0 = d[3 + t][0], v1 = d[3 + t][1];
-                            const double recv = __shfl_xor_sync(0xffffffffu, odd ? v0 : v1, 4);
-                            if ( odd ) v0 = recv; else v1 = recv;
-                            d[6 + t][0] = __shfl_sync(0xffffffffu, v0, src);
-                            d[6 + t][1] = __shfl_sync(0xffffffffu, v1, src);
-                        }
-                    }
                     const bool v0 = ( pp & 0xFFFFu ) != 0xFFFFu, v1 = ( pp >> 16 ) != 0xFFFFu;
                     // a first touch overwrites: the old value is then not read
                     const bool l0 = v0 && !( pp & 0x8000u ), l1 = v1 && !( pp & 0x80000000u );
-                    double *const p0 = sh.acc + ( pp & 0x7FFFu ), *const p1 = sh.acc + ( ( pp >> 16 ) & 0x7FFFu );
+                    // planes 0..5: entries (0,0) (1,1) (2,2) (0,1) (0,2) (1,2); planes 6..8: (1,0) (2,0) (2,1) of blocks whose column
+                    // node is outside the cluster.  A row-owning lane starts at plane 0, the others at plane 6 with products 3..5.
+                    double *const p0 = sh.acc + ( rown ? 0 : 6 * kPlane ) + ( pp & 0x7FFFu );
+                    double *const p1 = sh.acc + ( rown ? 0 : 6 * kPlane ) + ( ( pp >> 16 ) & 0x7FFFu );
                     // wait until every earlier element sharing a cluster node with this one has been added
                     if ( nd )
                         while ( sh.done[lane] < nd ) { }
                     __syncwarp();
                     __threadfence_block();
-                    // planes 3i+j: (0,0) (1,1) (2,2) (0,1) (0,2) (1,2) (1,0) (2,0) (2,1).  All loads first, then the additions,
-                    // then the stores: the positions of one lane are distinct.
-                    constexpr int kPl[9] = { 0, 4, 8, 1, 2, 5, 3, 6, 7 };
-                    double o0[9], o1[9];
+                    // All loads first, then the additions, then the stores: the positions of one lane are distinct.
+                    double o0[6], o1[6];
 #pragma unroll
-                    for ( int t = 0; t < 9; t++ ) {
+                    for ( int t = 0; t < 6; t++ ) {
                         o0[t] = 0.0;
                         o1[t] = 0.0;
-                        if ( l0 ) o0[t] = p0[kPl[t] * kPlane];
-                        if ( l1 ) o1[t] = p1[kPl[t] * kPlane];
+                        if ( t < 3 || rown ) {
+                            if ( l0 ) o0[t] = p0[t * kPlane];
+                            if ( l1 ) o1[t] = p1[t * kPlane];
+                        }
                     }
 #pragma unroll
-                    for ( int t = 0; t < 9; t++ ) {
-                        if ( v0 ) p0[kPl[t] * kPlane] = o0[t] + d[t][0];
-                        if ( v1 ) p1[kPl[t] * kPlane] = o1[t] + d[t][1];
+                    for ( int t = 0; t < 3; t++ ) {
+                        const double x0 = rown ? d[t][0] : d[3 + t][0], x1 = rown ? d[t][1] : d[3 + t][1];
+                        if ( v0 ) p0[t * kPlane] = o0[t] + x0;
+                        if ( v1 ) p1[t * kPlane] = o1[t] + x1;
+                    }
+#pragma unroll
+                    for ( int t = 3; t < 6; t++ ) {
+                        if ( rown && v0 ) p0[t * kPlane] = o0[t] + d[t][0];
+                        if ( rown && v1 ) p1[t * kPlane] = o1[t] + d[t][1];
                     }
                 }
                 mydone++;
@@ -936,34 +954,58 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             // ---- flush: one thread per 3x3 block, in row order (consecutive threads write consecutive column blocks of a node) ----
             const double lam = blob.lam, mu = blob.mu;
             const bool add = ACCUM || ( step.flags & 1 );
-            for ( int q = tid; q < step.nblocks; q += kCWarps * 32 ) {
-                const uint32_t info = blob.postab[q];
-                const int p = info & 0x7FF, cstart = ( info >> 11 ) & 0xFF, cm = ( info >> 19 ) & 7;
-                const int4 rb = *reinterpret_cast< const int4 * >( blob.rowbase[info >> 22] );
-                double g[9];
-#pragma unroll
-                for ( int c = 0; c < 9; c++ ) g[c] = sh.acc[c * kPlane + p];
-                const double tr = mu * ( g[0] + g[4] + g[8] );
-                double kb[9];
-                kb[0] = lam * g[0] + mu * g[0] + tr; kb[1] = lam * g[1] + mu * g[3];      kb[2] = lam * g[2] + mu * g[6];
-                kb[3] = lam * g[3] + mu * g[1];      kb[4] = lam * g[4] + mu * g[4] + tr; kb[5] = lam * g[5] + mu * g[7];
-                kb[6] = lam * g[6] + mu * g[2];      kb[7] = lam * g[7] + mu * g[5];      kb[8] = lam * g[8] + mu * g[8] + tr;
+            for ( int k = wid; k < step.nnodes; k += kCWarps ) {
+                const int4 rb = *reinterpret_cast< const int4 * >( blob.rowbase[k] );
+                const int noff = rb.w & 0xFFFF, nb = rb.w >> 16;
                 const int rowb[3] = { rb.x, rb.y, rb.z };
+                int ccarry = 0;
+                for ( int n0 = 0; n0 < nb; n0 += 32 ) {
+                    const int n = n0 + lane;
+                    const uint32_t info = n < nb ? blob.postab[noff + n] : 0u;
+                    const int cm = ( info >> 22 ) & 7, width = __popc(cm);
+                    int incl = width;                       // column offset of the block in its row: scan of the widths
 #pragma unroll
-                for ( int i = 0; i < 3; i++ ) {
-                    if ( rowb[i] < 0 ) continue;
-                    double *dst = val + rowb[i] + cstart;
-                    if ( cm == 7 ) {
-                        if ( add ) { dst[0] += kb[3 * i]; dst[1] += kb[3 * i + 1]; dst[2] += kb[3 * i + 2]; }
-                        else { dst[0] = kb[3 * i]; dst[1] = kb[3 * i + 1]; dst[2] = kb[3 * i + 2]; }
-                    } else {
-                        int c = 0;
+                    for ( int o = 1; o < 32; o <<= 1 ) {
+                        const int tsh = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ( lane >= o ) incl += tsh;
+                    }
+                    const int cstart = ccarry + incl - width;
+                    ccarry += __shfl_sync(0xffffffffu, incl, 31);
+                    if ( n >= nb ) continue;
+                    const double *pa = sh.acc + ( info & 0x7FF );
+                    // entries below the diagonal: from the transposed block if its row node is in the cluster, else from planes 6..8
+                    const double *pl = ( info >> 25 ) & 1 ? sh.acc + 3 * kPlane + ( ( info >> 11 ) & 0x7FF ) : pa + 6 * kPlane;
+                    double g[9];
+                    g[0] = pa[0];
+                    g[4] = pa[kPlane];
+                    g[8] = pa[2 * kPlane];
+                    g[1] = pa[3 * kPlane];
+                    g[2] = pa[4 * kPlane];
+                    g[5] = pa[5 * kPlane];
+                    g[3] = pl[0];
+                    g[6] = pl[kPlane];
+                    g[7] = pl[2 * kPlane];
+                    const double tr = mu * ( g[0] + g[4] + g[8] );
+                    double kb[9];
+                    kb[0] = lam * g[0] + mu * g[0] + tr; kb[1] = lam * g[1] + mu * g[3];      kb[2] = lam * g[2] + mu * g[6];
+                    kb[3] = lam * g[3] + mu * g[1];      kb[4] = lam * g[4] + mu * g[4] + tr; kb[5] = lam * g[5] + mu * g[7];
+                    kb[6] = lam * g[6] + mu * g[2];      kb[7] = lam * g[7] + mu * g[5];      kb[8] = lam * g[8] + mu * g[8] + tr;
 #pragma unroll
-                        for ( int j = 0; j < 3; j++ )
-                            if ( cm & ( 1 << j ) ) {
-                                dst[c] = add ? dst[c] + kb[3 * i + j] : kb[3 * i + j];
-                                c++;
-                            }
+                    for ( int i = 0; i < 3; i++ ) {
+                        if ( rowb[i] < 0 ) continue;
+                        double *dst = val + rowb[i] + cstart;
+                        if ( cm == 7 ) {
+                            if ( add ) { dst[0] += kb[3 * i]; dst[1] += kb[3 * i + 1]; dst[2] += kb[3 * i + 2]; }
+                            else { dst[0] = kb[3 * i]; dst[1] = kb[3 * i + 1]; dst[2] = kb[3 * i + 2]; }
+                        } else {
+                            int c = 0;
+#pragma unroll
+                            for ( int j = 0; j < 3; j++ )
+                                if ( cm & ( 1 << j ) ) {
+                                    dst[c] = add ? dst[c] + kb[3 * i + j] : kb[3 * i + j];
+                                    c++;
+                                }
+                        }
                     }
                 }
             }
