@@ -57,6 +57,10 @@ constexpr int kClMaxCell = 2048;             // most nodes in one spatial cell (
 #ifndef OB200_CL_HSLOTS
 #define OB200_CL_HSLOTS 6
 #endif
+#ifndef OB200_CL_ABLATE
+#define OB200_CL_ABLATE 0
+#endif
+constexpr int kAblate = OB200_CL_ABLATE;     // scratch (timing experiments only): 1 no accumulate, 2 no products, 4 no flush, 8 no geometry, 16 no dependency wait
 constexpr int kCWarps = OB200_CL_CWARPS;     // contraction warps
 constexpr int kGWarps = OB200_CL_GWARPS;     // geometry warps
 constexpr int kClThreads = ( kCWarps + 1 + kGWarps ) * 32;
@@ -80,6 +84,9 @@ struct ClRecord {                            // one (cluster, element) incidence
 };
 static_assert( sizeof( ClRecord ) == 352, "record layout" );
 constexpr int kPacketBytes = 4 * (int) sizeof( ClRecord );
+constexpr int kChunkPk = 4;                  // packets per bulk copy (one producer thread: fewer, larger copies)
+constexpr int kChunks = kRecSlots / kChunkPk;
+static_assert( kRecSlots % kChunkPk == 0, "record ring holds whole chunks" );
 
 struct ClStep {                              // elements of one material of one cluster
     int32_t rec_begin, npk;                  // first record, packets (4 records each)
@@ -89,9 +96,10 @@ struct ClStep {                              // elements of one material of one 
     int32_t nblocks, nsteps;                 // positions per plane in use; steps of this cluster (valid in its first step)
 };
 // What the flush of a step needs, contiguous in HBM so that one bulk copy brings it into shared memory:
-// the header, per cluster node the start of its (up to 3) rows in val (-1: prescribed dof) and its first block | blocks << 16,
-// per block (A, B) (in row order: node after node, column block after column block) its position in the planes | position of
-// the transposed block (B, A) << 11 | free-dof mask of the column node << 22 | (B is a cluster node) << 25.
+// the header, per cluster node the start of its (up to 3) rows in val (-1: prescribed dof) and its first block (sign bit: some
+// column node of the row has prescribed dofs), per block (A, B) (in row order: node after node, column block after column
+// block) its position in the planes | position of the transposed block (B, A) << 11 | free-dof mask of the column node << 22 |
+// (B is a cluster node) << 25 | cluster-local index of A << 26.
 struct ClBlob {
     ClStep hdr;
     double lam, mu;                          // Lame constants of the step's material
@@ -616,13 +624,15 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
                     const int eq = nodeeq[(int64_t) w * 3 + i];
                     B.rowbase[k][i] = eq > 0 ? rowptr[eq - 1] : -1;
                 }
-                B.rowbase[k][3] = base | ( nb << 16 );
+                bool regular = true;
                 for ( int n = 0; n < nb; n++ ) {
                     const int cm = blk[(int64_t) w * maxblk + n] >> 8;
+                    regular = regular && cm == 7;
                     const int tb = sh.tbid[base + n];
                     B.postab[base + n] = (uint32_t) sh.bpos[base + n] | ( (uint32_t)( tb != 0xFFFF ? sh.bpos[tb] : 0 ) << 11 ) |
-                                         ( (uint32_t) cm << 22 ) | ( tb != 0xFFFF ? 1u << 25 : 0u );
+                                         ( (uint32_t) cm << 22 ) | ( tb != 0xFFFF ? 1u << 25 : 0u ) | ( (uint32_t) k << 26 );
                 }
+                B.rowbase[k][3] = base | ( regular ? 0 : (int) 0x80000000 );
             }
             __syncthreads();
         }
@@ -634,9 +644,9 @@ cl_records_kernel(int32_t nclusters, const int32_t *__restrict__ cl_begin, const
 struct ClShared {
     double acc[9 * kPlane];
     double H[kHSlots][4][kHStride];
-    ClRecord rec[kRecSlots][4];
+    ClRecord rec[kChunks][kChunkPk * 4];
     ClBlob blob[2];
-    unsigned long long full_p[kRecSlots], empty_r[kRecSlots], full_g[kHSlots], empty_h[kHSlots], blob_full[2], blob_empty[2];
+    unsigned long long full_p[kChunks], empty_r[kChunks], full_g[kHSlots], empty_h[kHSlots], blob_full[2], blob_empty[2];
     volatile unsigned int done[kCWarps];
 };
 
@@ -648,6 +658,10 @@ __device__ __forceinline__ void cl_mbar_init(unsigned long long *bar, int count)
 __device__ __forceinline__ void cl_mbar_arrive(unsigned long long *bar)
 {
     asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( cl_smem(bar) ) : "memory" );
+}
+__device__ __forceinline__ void cl_mbar_arrive_n(unsigned long long *bar, uint32_t n)
+{
+    asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"( cl_smem(bar) ), "r"( n ) : "memory" );
 }
 __device__ __forceinline__ void cl_mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
 {
@@ -789,9 +803,9 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
     ClShared &sh = *reinterpret_cast< ClShared * >( cl_smem_raw );
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if ( tid == 0 ) {
-        for ( int s = 0; s < kRecSlots; s++ ) {
+        for ( int s = 0; s < kChunks; s++ ) {
             cl_mbar_init(&sh.full_p[s], 1);
-            cl_mbar_init(&sh.empty_r[s], 4);
+            cl_mbar_init(&sh.empty_r[s], kChunkPk * 4);
         }
         for ( int s = 0; s < kHSlots; s++ ) {
             cl_mbar_init(&sh.full_g[s], 1);
@@ -809,7 +823,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
     if ( wid == kCWarps ) {
         // ---- producer: one thread streams the flush tables of every step and its record packets into shared memory ----
         if ( lane != 0 ) return;
-        unsigned int pseq = 0, bseq = 0;
+        unsigned int cseq = 0, bseq = 0;
         for ( ClWalk w(V); w.valid(); w.next(), bseq++ ) {
             const ClBlob *blob = V.blobs + w.st;
             const int rec_begin = blob->hdr.rec_begin, npk = blob->hdr.npk, nblocks = blob->hdr.nblocks;
@@ -818,12 +832,13 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             const uint32_t bytes = (uint32_t)( kBlobHead + ( ( nblocks * 4 + 15 ) & ~15 ) );
             cl_mbar_expect_tx(&sh.blob_full[b], bytes);
             cl_bulk_load(&sh.blob[b], blob, bytes, &sh.blob_full[b]);
-            for ( int k = 0; k < npk; k++, pseq++ ) {
-                const int s = pseq % kRecSlots;
-                const unsigned int round = pseq / kRecSlots;
+            for ( int k = 0; k < npk; k += kChunkPk, cseq++ ) {
+                const int s = cseq % kChunks, n = min(kChunkPk, npk - k);
+                const unsigned int round = cseq / kChunks;
                 if ( round > 0 ) cl_mbar_wait(&sh.empty_r[s], ( round - 1 ) & 1);
-                cl_mbar_expect_tx(&sh.full_p[s], kPacketBytes);
-                cl_bulk_load(sh.rec[s], V.recs + rec_begin + 4 * k, kPacketBytes, &sh.full_p[s]);
+                if ( n < kChunkPk ) cl_mbar_arrive_n(&sh.empty_r[s], ( kChunkPk - n ) * 4);      // the records a short chunk lacks
+                cl_mbar_expect_tx(&sh.full_p[s], n * kPacketBytes);
+                cl_bulk_load(sh.rec[s], V.recs + rec_begin + 4 * k, n * kPacketBytes, &sh.full_p[s]);
             }
         }
         return;
@@ -832,26 +847,28 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
     if ( wid > kCWarps ) {
         // ---- geometry warps: lane = 8 * (element of the packet) + Gauss point ----
         const int g = wid - kCWarps - 1;
-        unsigned int pseq = 0;
+        unsigned int pseq = 0, cseq0 = 0;
         for ( ClWalk w(V); w.valid(); w.next() ) {
             const int npk = V.blobs[w.st].hdr.npk;
             for ( int k = 0; k < npk; k++, pseq++ ) {
                 if ( (int)( pseq % kGWarps ) != g ) continue;
-                const int rs = pseq % kRecSlots, hs = pseq % kHSlots;
-                cl_mbar_wait(&sh.full_p[rs], ( pseq / kRecSlots ) & 1);
+                const unsigned int cseq = cseq0 + k / kChunkPk;
+                const int cs = cseq % kChunks, hs = pseq % kHSlots;
+                cl_mbar_wait(&sh.full_p[cs], ( cseq / kChunks ) & 1);
                 if ( pseq >= kHSlots ) cl_mbar_wait(&sh.empty_h[hs], ( pseq / kHSlots - 1 ) & 1);
-                const ClRecord &R = sh.rec[rs][lane >> 3];
-                if ( R.elem >= 0 ) cl_geometry(R.xyz, lane & 7, R.slotof, sh.H[hs][lane >> 3]);
+                const ClRecord &R = sh.rec[cs][( k % kChunkPk ) * 4 + ( lane >> 3 )];
+                if ( R.elem >= 0 && !( kAblate & 8 ) ) cl_geometry(R.xyz, lane & 7, R.slotof, sh.H[hs][lane >> 3]);
                 __syncwarp();
                 if ( lane == 0 ) cl_mbar_arrive(&sh.full_g[hs]);
             }
+            cseq0 += ( npk + kChunkPk - 1 ) / kChunkPk;
         }
         return;
     }
 
     // ---- contraction warps ----
     const int a = lane >> 2, bp = lane & 3, b0 = 2 * bp, b1 = b0 + 1;
-    unsigned int pseq0 = 0;                 // packet sequence number of the current step's first packet
+    unsigned int pseq0 = 0, cseq0 = 0;      // packet / chunk sequence numbers of the current step's first packet
     const int nmine = V.nclusters > (int) blockIdx.x ? ( V.nclusters - 1 - (int) blockIdx.x ) / (int) gridDim.x + 1 : 0;
     unsigned int bseq = 0;
     for ( int kcl = 0; kcl < nmine; kcl++ ) {
@@ -869,11 +886,11 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             const int nrec = step.npk * 4;
             unsigned int mydone = 0;
             for ( int r = wid; r < nrec; r += kCWarps ) {
-                const unsigned int pseq = pseq0 + ( r >> 2 );
-                const int rs = pseq % kRecSlots, hs = pseq % kHSlots;
-                cl_mbar_wait(&sh.full_p[rs], ( pseq / kRecSlots ) & 1);      // the records (bulk copy)
+                const unsigned int pseq = pseq0 + ( r >> 2 ), cseq = cseq0 + ( r >> 2 ) / kChunkPk;
+                const int rs = cseq % kChunks, hs = pseq % kHSlots;
+                cl_mbar_wait(&sh.full_p[rs], ( cseq / kChunks ) & 1);        // the records (bulk copy)
                 cl_mbar_wait(&sh.full_g[hs], ( pseq / kHSlots ) & 1);        // the gradients (geometry warp)
-                const ClRecord &R = sh.rec[rs][r & 3];
+                const ClRecord &R = sh.rec[rs][r % ( kChunkPk * 4 )];
                 if ( R.elem >= 0 ) {
                     const double *H = sh.H[hs][r & 3] + 12 * a + bp;
                     // fragments: h[i][ks] = H[ks][3a+i][bp] -- both the A fragment of component i and the B fragment of component i
@@ -896,7 +913,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
 #pragma unroll
                     for ( int t = 0; t < 6; t++ ) d[t][0] = d[t][1] = 0.0;
 #pragma unroll
-                    for ( int ks = 0; ks < 2; ks++ ) {
+                    for ( int ks = 0; ks < ( ( kAblate & 2 ) ? 0 : 2 ); ks++ ) {
                         cl_dmma(d[0][0], d[0][1], h[0][ks], h[0][ks]);     // (0,0)
                         cl_dmma(d[1][0], d[1][1], h[1][ks], h[1][ks]);     // (1,1)
                         cl_dmma(d[2][0], d[2][1], h[2][ks], h[2][ks]);     // (2,2)
@@ -904,7 +921,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                         cl_dmma(d[4][0], d[4][1], h[0][ks], h[2][ks]);     // (0,2)
                         cl_dmma(d[5][0], d[5][1], h[1][ks], h[2][ks]);     // (1,2)
                     }
-                    const bool v0 = ( pp & 0xFFFFu ) != 0xFFFFu, v1 = ( pp >> 16 ) != 0xFFFFu;
+                    const bool v0 = ( pp & 0xFFFFu ) != 0xFFFFu && !( kAblate & 1 ), v1 = ( pp >> 16 ) != 0xFFFFu && !( kAblate & 1 );
                     // a first touch overwrites: the old value is then not read
                     const bool l0 = v0 && !( pp & 0x8000u ), l1 = v1 && !( pp & 0x80000000u );
                     // planes 0..5: entries (0,0) (1,1) (2,2) (0,1) (0,2) (1,2); planes 6..8: (1,0) (2,0) (2,1) of blocks whose column
@@ -912,8 +929,8 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                     double *const p0 = sh.acc + ( rown ? 0 : 6 * kPlane ) + ( pp & 0x7FFFu );
                     double *const p1 = sh.acc + ( rown ? 0 : 6 * kPlane ) + ( ( pp >> 16 ) & 0x7FFFu );
                     // wait until every earlier element sharing a cluster node with this one has been added
-                    if ( nd )
-                        while ( sh.done[lane] < nd ) { }
+                    if ( nd && !( kAblate & 16 ) )
+                        while ( sh.done[lane] < nd ) __nanosleep(20);
                     __syncwarp();
                     __threadfence_block();
                     // All loads first, then the additions, then the stores: the positions of one lane are distinct.
@@ -949,63 +966,57 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                 }
             }
             pseq0 += step.npk;
+            cseq0 += ( step.npk + kChunkPk - 1 ) / kChunkPk;
             asm volatile( "bar.sync 1, %0;" ::"n"( kCWarps * 32 ) : "memory" );
 
             // ---- flush: one thread per 3x3 block, in row order (consecutive threads write consecutive column blocks of a node) ----
             const double lam = blob.lam, mu = blob.mu;
             const bool add = ACCUM || ( step.flags & 1 );
-            for ( int k = wid; k < step.nnodes; k += kCWarps ) {
-                const int4 rb = *reinterpret_cast< const int4 * >( blob.rowbase[k] );
-                const int noff = rb.w & 0xFFFF, nb = rb.w >> 16;
+            for ( int q = tid; q < ( ( kAblate & 4 ) ? 0 : step.nblocks ); q += kCWarps * 32 ) {
+                const uint32_t info = blob.postab[q];
+                const int cm = ( info >> 22 ) & 7;
+                const int4 rb = *reinterpret_cast< const int4 * >( blob.rowbase[info >> 26] );
+                const int noff = rb.w & 0xFFFF;
+                // column offset of the block in its row: three per block unless a neighbouring node has prescribed dofs
+                int cstart = 3 * ( q - noff );
+                if ( rb.w < 0 ) {
+                    cstart = 0;
+                    for ( int n = noff; n < q; n++ ) cstart += __popc(( blob.postab[n] >> 22 ) & 7u);
+                }
+                const double *pa = sh.acc + ( info & 0x7FF );
+                // entries below the diagonal: from the transposed block if its row node is in the cluster, else from planes 6..8
+                const double *pl = ( info >> 25 ) & 1 ? sh.acc + 3 * kPlane + ( ( info >> 11 ) & 0x7FF ) : pa + 6 * kPlane;
+                double g[9];
+                g[0] = pa[0];
+                g[4] = pa[kPlane];
+                g[8] = pa[2 * kPlane];
+                g[1] = pa[3 * kPlane];
+                g[2] = pa[4 * kPlane];
+                g[5] = pa[5 * kPlane];
+                g[3] = pl[0];
+                g[6] = pl[kPlane];
+                g[7] = pl[2 * kPlane];
+                const double tr = mu * ( g[0] + g[4] + g[8] );
+                double kb[9];
+                kb[0] = lam * g[0] + mu * g[0] + tr; kb[1] = lam * g[1] + mu * g[3];      kb[2] = lam * g[2] + mu * g[6];
+                kb[3] = lam * g[3] + mu * g[1];      kb[4] = lam * g[4] + mu * g[4] + tr; kb[5] = lam * g[5] + mu * g[7];
+                kb[6] = lam * g[6] + mu * g[2];      kb[7] = lam * g[7] + mu * g[5];      kb[8] = lam * g[8] + mu * g[8] + tr;
                 const int rowb[3] = { rb.x, rb.y, rb.z };
-                int ccarry = 0;
-                for ( int n0 = 0; n0 < nb; n0 += 32 ) {
-                    const int n = n0 + lane;
-                    const uint32_t info = n < nb ? blob.postab[noff + n] : 0u;
-                    const int cm = ( info >> 22 ) & 7, width = __popc(cm);
-                    int incl = width;                       // column offset of the block in its row: scan of the widths
 #pragma unroll
-                    for ( int o = 1; o < 32; o <<= 1 ) {
-                        const int tsh = __shfl_up_sync(0xffffffffu, incl, o);
-                        if ( lane >= o ) incl += tsh;
-                    }
-                    const int cstart = ccarry + incl - width;
-                    ccarry += __shfl_sync(0xffffffffu, incl, 31);
-                    if ( n >= nb ) continue;
-                    const double *pa = sh.acc + ( info & 0x7FF );
-                    // entries below the diagonal: from the transposed block if its row node is in the cluster, else from planes 6..8
-                    const double *pl = ( info >> 25 ) & 1 ? sh.acc + 3 * kPlane + ( ( info >> 11 ) & 0x7FF ) : pa + 6 * kPlane;
-                    double g[9];
-                    g[0] = pa[0];
-                    g[4] = pa[kPlane];
-                    g[8] = pa[2 * kPlane];
-                    g[1] = pa[3 * kPlane];
-                    g[2] = pa[4 * kPlane];
-                    g[5] = pa[5 * kPlane];
-                    g[3] = pl[0];
-                    g[6] = pl[kPlane];
-                    g[7] = pl[2 * kPlane];
-                    const double tr = mu * ( g[0] + g[4] + g[8] );
-                    double kb[9];
-                    kb[0] = lam * g[0] + mu * g[0] + tr; kb[1] = lam * g[1] + mu * g[3];      kb[2] = lam * g[2] + mu * g[6];
-                    kb[3] = lam * g[3] + mu * g[1];      kb[4] = lam * g[4] + mu * g[4] + tr; kb[5] = lam * g[5] + mu * g[7];
-                    kb[6] = lam * g[6] + mu * g[2];      kb[7] = lam * g[7] + mu * g[5];      kb[8] = lam * g[8] + mu * g[8] + tr;
+                for ( int i = 0; i < 3; i++ ) {
+                    if ( rowb[i] < 0 ) continue;
+                    double *dst = val + rowb[i] + cstart;
+                    if ( cm == 7 ) {
+                        if ( add ) { dst[0] += kb[3 * i]; dst[1] += kb[3 * i + 1]; dst[2] += kb[3 * i + 2]; }
+                        else { dst[0] = kb[3 * i]; dst[1] = kb[3 * i + 1]; dst[2] = kb[3 * i + 2]; }
+                    } else {
+                        int c = 0;
 #pragma unroll
-                    for ( int i = 0; i < 3; i++ ) {
-                        if ( rowb[i] < 0 ) continue;
-                        double *dst = val + rowb[i] + cstart;
-                        if ( cm == 7 ) {
-                            if ( add ) { dst[0] += kb[3 * i]; dst[1] += kb[3 * i + 1]; dst[2] += kb[3 * i + 2]; }
-                            else { dst[0] = kb[3 * i]; dst[1] = kb[3 * i + 1]; dst[2] = kb[3 * i + 2]; }
-                        } else {
-                            int c = 0;
-#pragma unroll
-                            for ( int j = 0; j < 3; j++ )
-                                if ( cm & ( 1 << j ) ) {
-                                    dst[c] = add ? dst[c] + kb[3 * i + j] : kb[3 * i + j];
-                                    c++;
-                                }
-                        }
+                        for ( int j = 0; j < 3; j++ )
+                            if ( cm & ( 1 << j ) ) {
+                                dst[c] = add ? dst[c] + kb[3 * i + j] : kb[3 * i + j];
+                                c++;
+                            }
                     }
                 }
             }
