@@ -423,8 +423,9 @@ def run_ours(args):
     layout = (C.c_int64 * 3)()
     check(lib().ob200_csr_spmv_layout(A.h, layout))
     blocked, nrb, nblk = int(layout[0]), int(layout[1]), int(layout[2])
-    asm_name = next((k for k in ("lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
-                                 "lspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_gather_kernel< false >")
+    asm_name = next((k for k in ("lspace_cluster_kernel< false >", "lspace_cluster_kernel< true >",
+                                 "lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
+                                 "lspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_cluster_kernel< false >")
     ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
     ms_asmk, n_asmk = prof.get(asm_name, (0.0, 0))
     # algorithmic bytes: SpMV reads val (8 B) + colind (4 B) per non-zero, and per
@@ -447,7 +448,7 @@ def run_ours(args):
         traffic = {}
     full_size = (nx, ny, nz) == (250, 64, 64)         # the captures were taken at this size
     spmv_traffic = traffic.get(spmv_name.split("<")[0].strip()) if full_size else None
-    asm_traffic = traffic.get("lspace_gather_kernel") if full_size and asm_name.startswith("lspace_gather") else None
+    asm_traffic = traffic.get(asm_name.split("<")[0].strip()) if full_size else None
     kernel_share = {k: round(v[0] / (t_step * args.steps) , 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
 
     cpu = None
@@ -484,7 +485,8 @@ def run_ours(args):
         "roofline_assembly": {"kernel": asm_name, "bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s",
                               "frac": asm_gbs / peak, "traffic": asm_traffic, "algorithmic_bytes_per_launch": asm_bytes,
                               "avg_launch_ms": asm_dur * 1e3, "launches": n_asmk,
-                              "note": "owner-computes gather; FP64-pipe bound, see DESIGN.md"},
+                              "traffic_source": "profiles/traffic.json (committed ncu --set full capture at this size); not measured in this run",
+                              "note": "cluster assembly (assemble_cluster.cu): shared-memory / dependency-chain bound, see DESIGN.md 3.3"},
         "kernel_time_share": kernel_share,
         "e2e": {"value": total_elems / e_asm, "unit": "elements/s", "pcg_iters_per_s": args.cg_iters / e_cg,
                 "h2d_bytes_per_step": int(h2d_asm + h2d_cg), "d2h_bytes_per_step": int(d2h_cg),

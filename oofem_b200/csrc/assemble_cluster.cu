@@ -55,11 +55,18 @@ constexpr int kClMaxCell = 2048;             // most nodes in one spatial cell (
 #define OB200_CL_RECSLOTS 16
 #endif
 #ifndef OB200_CL_HSLOTS
-#define OB200_CL_HSLOTS 6
+#define OB200_CL_HSLOTS 8
+#endif
+#ifndef OB200_CL_FLUSH_UNROLL
+#define OB200_CL_FLUSH_UNROLL 2
+#endif
+#ifndef OB200_CL_SPIN_NS
+#define OB200_CL_SPIN_NS 20
 #endif
 #ifndef OB200_CL_ABLATE
 #define OB200_CL_ABLATE 0
 #endif
+constexpr int kFlushUnroll = OB200_CL_FLUSH_UNROLL;
 constexpr int kAblate = OB200_CL_ABLATE;     // scratch (timing experiments only): 1 no accumulate, 2 no products, 4 no flush, 8 no geometry, 16 no dependency wait
 constexpr int kCWarps = OB200_CL_CWARPS;     // contraction warps
 constexpr int kGWarps = OB200_CL_GWARPS;     // geometry warps
@@ -648,6 +655,7 @@ struct ClShared {
     ClBlob blob[2];
     unsigned long long full_p[kChunks], empty_r[kChunks], full_g[kHSlots], empty_h[kHSlots], blob_full[2], blob_empty[2];
     volatile unsigned int done[kCWarps];
+    volatile unsigned int failed;            // a bounded wait ran out
 };
 
 __device__ __forceinline__ uint32_t cl_smem(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -667,17 +675,40 @@ __device__ __forceinline__ void cl_mbar_expect_tx(unsigned long long *bar, uint3
 {
     asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( cl_smem(bar) ), "r"( bytes ) : "memory" );
 }
-__device__ __forceinline__ void cl_mbar_wait(unsigned long long *bar, uint32_t parity)
+// Every wait in the kernel is bounded (about 2 s): a schedule or hardware fault then ends the launch with the error word set
+// instead of hanging the GPU; cluster_assemble_lspace reports it as OB200_ECUDA.
+__device__ int *cl_error_word = nullptr;
+__device__ __forceinline__ void cl_fail(int code)
 {
+    if ( cl_error_word ) atomicExch(cl_error_word, code);
+}
+#ifndef OB200_CL_WAIT_HINT_NS
+#define OB200_CL_WAIT_HINT_NS 20000
+#endif
+#ifndef OB200_CL_BOUNDED
+#define OB200_CL_BOUNDED 1
+#endif
+constexpr unsigned int kClSpinLimit = OB200_CL_BOUNDED ? 1u << 20 : 0xFFFFFFFFu;      // try_wait rounds (each suspends for a hardware-defined time) / polls
+__device__ __forceinline__ void cl_mbar_wait(unsigned long long *bar, uint32_t parity, volatile unsigned int *failed)
+{
+    // try_wait suspends the thread until the phase completes or the time hint (ns) runs out: the loop body runs rarely, so the
+    // round counter that bounds the wait costs nothing while other warps work
+    uint32_t ok;
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n"
         "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 q, n, %3;\n"
+        "@q bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"( cl_smem(bar) ), "r"( parity ) : "memory" );
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"( ok ) : "r"( cl_smem(bar) ), "r"( parity ), "r"( kClSpinLimit ), "r"( (uint32_t) OB200_CL_WAIT_HINT_NS ) : "memory" );
+    if ( !ok ) *failed = 1u;      // shared-memory word, reported when the role's loop ends (cl_fail)
 }
 __device__ __forceinline__ void cl_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
@@ -818,6 +849,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
         asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
     }
     if ( tid < kCWarps ) sh.done[tid] = 0;
+    if ( tid == 0 ) sh.failed = 0;
     __syncthreads();
 
     if ( wid == kCWarps ) {
@@ -828,19 +860,20 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             const ClBlob *blob = V.blobs + w.st;
             const int rec_begin = blob->hdr.rec_begin, npk = blob->hdr.npk, nblocks = blob->hdr.nblocks;
             const int b = bseq & 1;
-            if ( bseq >= 2 ) cl_mbar_wait(&sh.blob_empty[b], ( ( bseq >> 1 ) - 1 ) & 1);
+            if ( bseq >= 2 ) cl_mbar_wait(&sh.blob_empty[b], ( ( bseq >> 1 ) - 1 ) & 1, &sh.failed);
             const uint32_t bytes = (uint32_t)( kBlobHead + ( ( nblocks * 4 + 15 ) & ~15 ) );
             cl_mbar_expect_tx(&sh.blob_full[b], bytes);
             cl_bulk_load(&sh.blob[b], blob, bytes, &sh.blob_full[b]);
             for ( int k = 0; k < npk; k += kChunkPk, cseq++ ) {
                 const int s = cseq % kChunks, n = min(kChunkPk, npk - k);
                 const unsigned int round = cseq / kChunks;
-                if ( round > 0 ) cl_mbar_wait(&sh.empty_r[s], ( round - 1 ) & 1);
+                if ( round > 0 ) cl_mbar_wait(&sh.empty_r[s], ( round - 1 ) & 1, &sh.failed);
                 if ( n < kChunkPk ) cl_mbar_arrive_n(&sh.empty_r[s], ( kChunkPk - n ) * 4);      // the records a short chunk lacks
                 cl_mbar_expect_tx(&sh.full_p[s], n * kPacketBytes);
                 cl_bulk_load(sh.rec[s], V.recs + rec_begin + 4 * k, n * kPacketBytes, &sh.full_p[s]);
             }
         }
+        if ( sh.failed ) cl_fail((int) sh.failed);
         return;
     }
 
@@ -854,8 +887,8 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                 if ( (int)( pseq % kGWarps ) != g ) continue;
                 const unsigned int cseq = cseq0 + k / kChunkPk;
                 const int cs = cseq % kChunks, hs = pseq % kHSlots;
-                cl_mbar_wait(&sh.full_p[cs], ( cseq / kChunks ) & 1);
-                if ( pseq >= kHSlots ) cl_mbar_wait(&sh.empty_h[hs], ( pseq / kHSlots - 1 ) & 1);
+                cl_mbar_wait(&sh.full_p[cs], ( cseq / kChunks ) & 1, &sh.failed);
+                if ( pseq >= kHSlots ) cl_mbar_wait(&sh.empty_h[hs], ( pseq / kHSlots - 1 ) & 1, &sh.failed);
                 const ClRecord &R = sh.rec[cs][( k % kChunkPk ) * 4 + ( lane >> 3 )];
                 if ( R.elem >= 0 && !( kAblate & 8 ) ) cl_geometry(R.xyz, lane & 7, R.slotof, sh.H[hs][lane >> 3]);
                 __syncwarp();
@@ -863,6 +896,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             }
             cseq0 += ( npk + kChunkPk - 1 ) / kChunkPk;
         }
+        if ( sh.failed ) cl_fail((int) sh.failed);
         return;
     }
 
@@ -875,7 +909,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
         bool last = false;
         while ( !last ) {
             const int bb = bseq & 1;
-            cl_mbar_wait(&sh.blob_full[bb], ( bseq >> 1 ) & 1);
+            cl_mbar_wait(&sh.blob_full[bb], ( bseq >> 1 ) & 1, &sh.failed);
             const ClBlob &blob = sh.blob[bb];
             const ClStep step = blob.hdr;
             last = ( step.flags & 4 ) != 0;
@@ -888,8 +922,8 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             for ( int r = wid; r < nrec; r += kCWarps ) {
                 const unsigned int pseq = pseq0 + ( r >> 2 ), cseq = cseq0 + ( r >> 2 ) / kChunkPk;
                 const int rs = cseq % kChunks, hs = pseq % kHSlots;
-                cl_mbar_wait(&sh.full_p[rs], ( cseq / kChunks ) & 1);        // the records (bulk copy)
-                cl_mbar_wait(&sh.full_g[hs], ( pseq / kHSlots ) & 1);        // the gradients (geometry warp)
+                cl_mbar_wait(&sh.full_p[rs], ( cseq / kChunks ) & 1, &sh.failed);        // the records (bulk copy)
+                cl_mbar_wait(&sh.full_g[hs], ( pseq / kHSlots ) & 1, &sh.failed);        // the gradients (geometry warp)
                 const ClRecord &R = sh.rec[rs][r % ( kChunkPk * 4 )];
                 if ( R.elem >= 0 ) {
                     const double *H = sh.H[hs][r & 3] + 12 * a + bp;
@@ -929,8 +963,16 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                     double *const p0 = sh.acc + ( rown ? 0 : 6 * kPlane ) + ( pp & 0x7FFFu );
                     double *const p1 = sh.acc + ( rown ? 0 : 6 * kPlane ) + ( ( pp >> 16 ) & 0x7FFFu );
                     // wait until every earlier element sharing a cluster node with this one has been added
-                    if ( nd && !( kAblate & 16 ) )
-                        while ( sh.done[lane] < nd ) __nanosleep(20);
+                    if ( nd && !( kAblate & 16 ) ) {
+                        unsigned int spins = 0;
+                        while ( sh.done[lane] < nd ) {
+                            __nanosleep(OB200_CL_SPIN_NS);
+                            if ( ++spins > kClSpinLimit ) {
+                                sh.failed = 2u;
+                                break;
+                            }
+                        }
+                    }
                     __syncwarp();
                     __threadfence_block();
                     // All loads first, then the additions, then the stores: the positions of one lane are distinct.
@@ -972,6 +1014,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             // ---- flush: one thread per 3x3 block, in row order (consecutive threads write consecutive column blocks of a node) ----
             const double lam = blob.lam, mu = blob.mu;
             const bool add = ACCUM || ( step.flags & 1 );
+#pragma unroll ( kFlushUnroll )
             for ( int q = tid; q < ( ( kAblate & 4 ) ? 0 : step.nblocks ); q += kCWarps * 32 ) {
                 const uint32_t info = blob.postab[q];
                 const int cm = ( info >> 22 ) & 7;
@@ -1026,6 +1069,7 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             bseq++;
         }
     }
+    if ( sh.failed ) cl_fail((int) sh.failed);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -1168,6 +1212,21 @@ int cluster_assemble_lspace(ob200_elemset *S, ob200_csr *A)
     int grid = ctx->shape.sms;                          // persistent: one CTA per SM
     if ( grid > S->nclusters ) grid = S->nclusters;
     if ( A->zero_pending && !S->covers_all ) OB_CHECK( ob200_csr_materialize(A) );
+    // error word: a failure of the previous launch is reported now (and by ob200_context_sync); no host synchronisation here
+    if ( !ctx->kerr_dev ) {
+        OB_CUDA( cudaMalloc(&ctx->kerr_dev, sizeof( int )) );
+        OB_CUDA( cudaMallocHost((void **) &ctx->kerr_host, sizeof( int )) );
+        *ctx->kerr_host = 0;
+        OB_CUDA( cudaMemsetAsync(ctx->kerr_dev, 0, sizeof( int ), ctx->stream) );
+    }
+    if ( *ctx->kerr_host ) {
+        const int code = *ctx->kerr_host;
+        *ctx->kerr_host = 0;
+        OB_CUDA( cudaMemsetAsync(ctx->kerr_dev, 0, sizeof( int ), ctx->stream) );
+        OB_REQUIRE(false, OB200_ECUDA, "cluster assembly: a wait inside the previous launch timed out (code %d); its matrix values are invalid", code);
+    }
+    int *errp = ctx->kerr_dev;
+    OB_CUDA( cudaMemcpyToSymbolAsync(cl_error_word, &errp, sizeof( errp ), 0, cudaMemcpyHostToDevice, ctx->stream) );
     if ( A->zero_pending ) {
         // every entry of the pattern is written by exactly one lane: the pending zero() is absorbed
         OB_LAUNCH(ctx, lspace_cluster_kernel< false >, grid, kClThreads, smem, v, V, A->val.p);
@@ -1175,6 +1234,7 @@ int cluster_assemble_lspace(ob200_elemset *S, ob200_csr *A)
     } else {
         OB_LAUNCH(ctx, lspace_cluster_kernel< true >, grid, kClThreads, smem, v, V, A->val.p);
     }
+    OB_CUDA( cudaMemcpyAsync((void *) ctx->kerr_host, ctx->kerr_dev, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
     return OB200_OK;
 }
 

@@ -128,6 +128,10 @@ struct ob200_context {
     ob200::DevBuf< char > flush;
     // reduction scratch (partials) and small device scalars, used by CG
     ob200::DevBuf< double > partials;
+    // error word of the kernels whose waits are bounded (assemble_cluster.cu): device word + pinned host copy that follows
+    // every such launch on the stream; looked at by the next call of that kind and by ob200_context_sync
+    int *kerr_dev = nullptr;
+    volatile int *kerr_host = nullptr;
 };
 
 namespace ob200 {

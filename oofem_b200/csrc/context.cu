@@ -97,6 +97,8 @@ void ob200_context_destroy(ob200_context *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->flush.release();
     ctx->partials.release();
+    if ( ctx->kerr_dev ) cudaFree(ctx->kerr_dev);
+    if ( ctx->kerr_host ) cudaFreeHost((void *) ctx->kerr_host);
     cudaStreamSynchronize(ctx->stream);
     stream_register(ctx->stream, false);
     if ( current_stream().stream == ctx->stream ) current_stream().stream = nullptr;
@@ -112,6 +114,12 @@ int ob200_context_sync(ob200_context *ctx)
     if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx, OB200_EINVAL, "context_sync: null context");
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    if ( ctx->kerr_host && *ctx->kerr_host ) {
+        const int code = *ctx->kerr_host;
+        *ctx->kerr_host = 0;
+        cudaMemsetAsync(ctx->kerr_dev, 0, sizeof( int ), ctx->stream);
+        OB_REQUIRE(false, OB200_ECUDA, "a wait inside an assembly kernel timed out (code %d); the matrix values are invalid", code);
+    }
     return OB200_OK;
 }
 
