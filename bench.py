@@ -379,9 +379,10 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 3))
     if args.no_e2e:                 # profiling runs (ncu) only; never used for a reported line
         ts = [(float("nan"), float("nan"))]
+        cold = ts[0]
         e2e_steps = 1
     else:
-        step_e2e()
+        cold = step_e2e()           # first upload of this mesh: builds the assembly schedule (kept by the context afterwards)
         barrier()
         ts = [step_e2e() for _ in range(e2e_steps)]
         barrier()
@@ -490,7 +491,11 @@ def run_ours(args):
         "kernel_time_share": kernel_share,
         "e2e": {"value": total_elems / e_asm, "unit": "elements/s", "pcg_iters_per_s": args.cg_iters / e_cg,
                 "h2d_bytes_per_step": int(h2d_asm + h2d_cg), "d2h_bytes_per_step": int(d2h_cg),
-                "ms_assembly": e_asm * 1e3, "ms_pcg": e_cg * 1e3},
+                "ms_assembly": e_asm * 1e3, "ms_pcg": e_cg * 1e3,
+                "ms_assembly_first_upload": cold[0] * 1e3,
+                "note": "every step uploads the mesh arrays again (211 MB H2D) and creates a new element set; the assembly "
+                        "schedule of an unchanged mesh is recognised by content hash and reused (ms_assembly_first_upload = "
+                        "the step that builds it, rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
     }
     if cpu is not None:

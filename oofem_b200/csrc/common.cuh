@@ -92,6 +92,16 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if ( this != &o ) {
+            release();
+            p = o.p; n = o.n; s = o.s;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
 };
 
 } // namespace ob200
@@ -132,6 +142,10 @@ struct ob200_context {
     // every such launch on the stream; looked at by the next call of that kind and by ob200_context_sync
     int *kerr_dev = nullptr;
     volatile int *kerr_host = nullptr;
+    // assembly schedule of the last element set that was destroyed (element_kernels.cu): an element set created from the
+    // same mesh, numbering and materials adopts it instead of rebuilding it
+    void *sched_cache = nullptr;
+    void ( *sched_cache_free )(void *) = nullptr;
 };
 
 namespace ob200 {

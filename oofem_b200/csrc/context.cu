@@ -97,6 +97,11 @@ void ob200_context_destroy(ob200_context *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->flush.release();
     ctx->partials.release();
+    if ( ctx->sched_cache && ctx->sched_cache_free ) {
+        ob200::bind_stream(ctx);
+        ctx->sched_cache_free(ctx->sched_cache);
+        ctx->sched_cache = nullptr;
+    }
     if ( ctx->kerr_dev ) cudaFree(ctx->kerr_dev);
     if ( ctx->kerr_host ) cudaFreeHost((void *) ctx->kerr_host);
     cudaStreamSynchronize(ctx->stream);

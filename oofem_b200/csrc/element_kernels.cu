@@ -5,6 +5,9 @@
 // giveInternalForcesVector (src/sm/Elements/structuralelement.C:575-643, 724-802).
 #include "element_device.cuh"
 #include "elemset.h"
+#include <stdlib.h>
+#include <string.h>
+#include <utility>
 
 namespace ob200 {
 
@@ -382,6 +385,49 @@ static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe,
     return OB200_OK;
 }
 
+// ---- schedule cache -----------------------------------------------------------------------------------
+// Content hash of an array of 32-bit words: sum over i of mix(i, a[i]) (integer additions: order independent, so the
+// result does not depend on how the grid happens to be scheduled).
+__global__ void content_hash_kernel(const uint32_t *__restrict__ a, int64_t n, unsigned long long salt, unsigned long long *__restrict__ out)
+{
+    unsigned long long acc = 0;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride ) {
+        unsigned long long z = ( (unsigned long long) i * 0x9E3779B97F4A7C15ull ) ^ ( (unsigned long long) a[i] * 0xD6E8FEB86659FD93ull ) ^ salt;
+        z = ( z ^ ( z >> 30 ) ) * 0xBF58476D1CE4E5B9ull;
+        z = ( z ^ ( z >> 27 ) ) * 0x94D049BB133111EBull;
+        acc += z ^ ( z >> 31 );
+    }
+#pragma unroll
+    for ( int o = 16; o > 0; o >>= 1 ) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ( ( threadIdx.x & 31 ) == 0 && acc ) atomicAdd(out, acc);
+}
+
+static void sched_cache_free(void *p) { delete static_cast< ob200_sched * >( p ); }
+
+// key of the schedule: sizes + content hashes of connectivity, location arrays, coordinates, material numbers and
+// material table (the records of the cluster assembly hold coordinates; the steps hold Lame constants)
+static int sched_key(ob200_elemset *S, unsigned long long key[8])
+{
+    ob200_context *ctx = S->ctx;
+    DevBuf< unsigned long long > h;
+    OB_CHECK( h.alloc(5) );
+    OB_CUDA( cudaMemsetAsync(h.p, 0, sizeof( unsigned long long ) * 5, ctx->stream) );
+    const void *arr[5] = { S->conn.p, S->loc.p, S->coords.p, S->matid.p, S->mat.p };
+    const int64_t words[5] = { S->nelem * S->nen, S->nelem * S->nd, S->nnode * 6, S->nelem, (int64_t) S->nmat * OB200_MATPARAM_STRIDE * 2 };
+    for ( int i = 0; i < 5; i++ )
+        if ( words[i] > 0 )
+            OB_LAUNCH(ctx, content_hash_kernel, ctx->shape.grid(words[i], 256, 8), 256, 0, (const uint32_t *) arr[i], words[i],
+                      (unsigned long long)( i + 1 ), h.p + i);
+    OB_CUDA( cudaMemcpyAsync(key, h.p, sizeof( unsigned long long ) * 5, cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    const char *env = getenv("OB200_ASSEMBLY");
+    key[5] = ( (unsigned long long) S->etype << 56 ) ^ ( (unsigned long long) S->nnode << 28 ) ^ (unsigned long long) S->nelem;
+    key[6] = ( (unsigned long long) (unsigned int) S->neq << 32 ) ^ (unsigned long long) S->nmat;
+    key[7] = env ? ( !strcmp(env, "gather") ? 1 : 2 ) : 0;
+    return OB200_OK;
+}
+
 } // namespace ob200
 
 using namespace ob200;
@@ -455,7 +501,27 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
             S->all_isole = false;
         }
     }
-    if ( ( rc = gather_prepare_mesh(S) ) < 0 ) { delete S; return rc; }
+    // the schedule of the last destroyed set is adopted if it was built from identical arrays (OB200_SCHED_CACHE=0 disables)
+    static const bool use_cache = !( getenv("OB200_SCHED_CACHE") && !strcmp(getenv("OB200_SCHED_CACHE"), "0") );
+    bool adopted = false;
+    if ( use_cache && nelem > 0 ) {
+        if ( ( rc = elemset_await_loc(S) ) < 0 ) { delete S; return rc; }
+        unsigned long long key[8];
+        if ( ( rc = sched_key(S, key) ) < 0 ) { delete S; return rc; }
+        ob200_sched *C = static_cast< ob200_sched * >( ctx->sched_cache );
+        if ( C && C->have_mesh && !memcmp(C->key, key, sizeof( key )) ) {
+            static_cast< ob200_sched & >( *S ) = std::move(*C);
+            delete C;
+            ctx->sched_cache = nullptr;
+            adopted = true;
+        }
+        memcpy(S->key, key, sizeof( key ));
+    }
+    if ( !adopted ) {
+        if ( ( rc = gather_prepare_mesh(S) ) < 0 ) { delete S; return rc; }
+        S->have_mesh = true;
+        S->have_bind = false;
+    }
     if ( ( rc = elemset_await_loc(S) ) < 0 ) { delete S; return rc; }
     if ( !on_device && cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess ) {      // the caller's host buffer is free again on return
         set_error("elemset_create: upload of the location arrays failed");
@@ -475,7 +541,18 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
     return OB200_OK;
 }
 
-void ob200_elemset_destroy(ob200_elemset *S) { delete S; }
+void ob200_elemset_destroy(ob200_elemset *S)
+{
+    if ( !S ) return;
+    // keep the schedule for an element set that may be created from the same arrays (a re-upload of an unchanged mesh)
+    if ( S->ctx && S->have_mesh && S->key[5] != 0 && stream_alive(S->ctx->stream) ) {
+        ob200::bind_stream(S->ctx);
+        if ( S->ctx->sched_cache ) sched_cache_free(S->ctx->sched_cache);
+        S->ctx->sched_cache = new ob200_sched(std::move(static_cast< ob200_sched & >( *S )));
+        S->ctx->sched_cache_free = sched_cache_free;
+    }
+    delete S;
+}
 
 int64_t ob200_elemset_size(const ob200_elemset *S) { return S ? S->nelem : 0; }
 
@@ -533,11 +610,16 @@ int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
     OB_REQUIRE(S && A, OB200_EINVAL, "elemset_bind: null argument");
     OB_REQUIRE(A->rowptr.p, OB200_EINVAL, "elemset_bind: matrix has no structure (call ob200_csr_build_structure first)");
     S->bound = nullptr;
-    S->slot_built = false;
-    // preferred: owner-computes gather (no atomics); its preparation also verifies that the
-    // matrix pattern is the one of this element set
-    OB_CHECK( gather_bind(S, A) );
-    if ( !S->gather_ok ) OB_CHECK( build_slot_map(S, A) );
+    if ( !( S->have_bind && S->bind_structure == A->structure_version ) ) {       // else: adopted from the schedule cache
+        S->have_bind = false;
+        S->slot_built = false;
+        // preferred: owner-computes assembly (no atomics); its preparation also verifies that the
+        // matrix pattern is the one of this element set
+        OB_CHECK( gather_bind(S, A) );
+        if ( !S->gather_ok ) OB_CHECK( build_slot_map(S, A) );
+        S->have_bind = true;
+        S->bind_structure = A->structure_version;
+    }
     S->bound = A;
     S->bound_version = A->structure_version;
     return OB200_OK;

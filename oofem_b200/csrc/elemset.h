@@ -53,16 +53,15 @@ struct ob200_csr {
     int64_t diag_version = -1;
 };
 
-struct ob200_elemset {
-    ob200_context *ctx = nullptr;
-    int etype = 0, nen = 0, ngp = 0, nd = 0;
-    int64_t nnode = 0, nelem = 0;
-    int32_t nmat = 0, neq = 0;
-    bool has_state = false;
-    ob200::DevBuf< double > coords, mat, state, exyz;
-    ob200::DevBuf< int32_t > conn, matid, loc, slot;
-    ob200_csr *bound = nullptr;
-    int64_t bound_version = -1;
+// Everything the assembly kernels derive from the mesh and its equation numbers (built at create) and from the sparsity
+// structure of the bound matrix (built at bind).  Kept apart from the element set so that it can outlive it: the context
+// caches the schedule of the last destroyed set, and a set created from identical arrays adopts it (ob200_elemset_create).
+struct ob200_sched {
+    bool have_mesh = false, have_bind = false;
+    int64_t bind_structure = -1;                   // structure_version of the matrix the bind part belongs to
+    unsigned long long key[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };   // content hashes + sizes of the arrays it was built from
+    ob200::DevBuf< double > exyz;
+    ob200::DevBuf< int32_t > slot;
     bool slot_built = false;
     // owner-computes ("gather") assembly, assemble_gather.cu: node -> element incidence, built at create
     int32_t maxval = 0;                            // largest number of elements around a node
@@ -81,6 +80,18 @@ struct ob200_elemset {
     ob200::DevBuf< unsigned char > ebidx, nloc, npar, cl_recs, cl_steps;
     ob200::DevBuf< unsigned short > nbase;
     ob200::DevBuf< int32_t > cnodes, ncl, cl_begin, cl_step;
+};
+
+struct ob200_elemset : ob200_sched {
+    ob200_context *ctx = nullptr;
+    int etype = 0, nen = 0, ngp = 0, nd = 0;
+    int64_t nnode = 0, nelem = 0;
+    int32_t nmat = 0, neq = 0;
+    bool has_state = false;
+    ob200::DevBuf< double > coords, mat, state;
+    ob200::DevBuf< int32_t > conn, matid, loc;
+    ob200_csr *bound = nullptr;
+    int64_t bound_version = -1;
     bool all_isole = true;
     bool loc_pending = false;                      // loc is still travelling on the context's copy stream
     int64_t neq_hint() const { return neq; }
