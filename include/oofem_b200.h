@@ -104,8 +104,16 @@ int  ob200_csr_scale(ob200_csr *A, double s);               /* SparseMtrx::times
  * plain per-element call the reference makes. */
 int  ob200_csr_assemble(ob200_csr *A, int64_t nelem, int32_t ndofel, const int32_t *loc,
                         const double *mat, int on_device);
+/* SparseMtrx::assemble(rloc, cloc, mat) (compcol.C:301-336): one rectangular block, mat [nr][nc] row-major; only the
+ * rloc x cloc entries are looked up */
+int  ob200_csr_assemble_rect(ob200_csr *A, int32_t nr, int32_t nc, const int32_t *rloc, const int32_t *cloc,
+                             const double *mat, int on_device);
 int  ob200_csr_times(ob200_csr *A, const double *x, double *y, int on_device);   /* SparseMtrx::times (compcol.C:119) */
-int  ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value);            /* SparseMtrx::at, 1-based (compcol.C:376) */
+/* SparseMtrx::timesT (compcol.C:146-163): y = A^T x */
+int  ob200_csr_times_t(ob200_csr *A, const double *x, double *y, int on_device);
+/* SparseMtrx::at, 1-based (compcol.C:376): returns 0 and the value if (i,j) is stored, 1 and value 0 if it is in bounds but not in
+ * the sparse structure (CompCol::at const; isAllocatedAt is false), OB200_EINVAL out of bounds */
+int  ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value);
 int64_t ob200_csr_version(const ob200_csr *A);              /* SparseMtrx::giveVersion */
 
 /* ---- batched element-evaluation hook ------------------------------------------------ */

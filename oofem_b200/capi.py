@@ -53,7 +53,9 @@ SYMBOLS = {
     "ob200_csr_zero": (_int, [_vp]),
     "ob200_csr_scale": (_int, [_vp, _dbl]),
     "ob200_csr_assemble": (_int, [_vp, _i64, _i32, _vp, _vp, _int]),
+    "ob200_csr_assemble_rect": (_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _int]),
     "ob200_csr_times": (_int, [_vp, _vp, _vp, _int]),
+    "ob200_csr_times_t": (_int, [_vp, _vp, _vp, _int]),
     "ob200_csr_at": (_int, [_vp, _i32, _i32, C.POINTER(_dbl)]),
     "ob200_csr_version": (_i64, [_vp]),
     "ob200_elemset_create": (_int, [_vp, _int, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _int, _pp]),

@@ -1000,6 +1000,8 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
 {
     ob200_context *ctx = S->ctx;
     S->gather_ok = false;
+    S->cluster_ok = false;
+    if ( getenv("OB200_ASSEMBLY") && !strcmp(getenv("OB200_ASSEMBLY"), "slotmap") ) return OB200_OK;      // generic path (cross-checks)
     if ( S->etype != OB200_LSPACE || S->nelem == 0 || !S->all_isole || !S->ninc.p ) return OB200_OK;
     if ( S->maxval > kMaxValence || A->maxrow > kMaxRowLen || A->neq == 0 ) return OB200_OK;
     S->maxblk = ( ( A->maxrow + 3 ) & ~3 );          // a column block is at least one column wide
@@ -1012,7 +1014,7 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     OB_CUDA( cudaMemsetAsync(flags.p, 0, sizeof( int ) * 4, ctx->stream) );
     OB_CUDA( cudaMemsetAsync(S->blk.p, 0, sizeof( unsigned short ) * (size_t) S->nnode * S->maxblk, ctx->stream) );
     OB_CHECK( S->ebidx.alloc(S->nvisit * 8) );
-    static const bool allpairs = getenv("OB200_NODE_BLOCKS") && !strcmp(getenv("OB200_NODE_BLOCKS"), "allpairs");
+    const bool allpairs = getenv("OB200_NODE_BLOCKS") && !strcmp(getenv("OB200_NODE_BLOCKS"), "allpairs");
     if ( allpairs ) {
         OB_LAUNCH(ctx, node_blocks_allpairs_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
                   S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,

@@ -471,7 +471,7 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
 
     // distributed: all-reduce the locally reduced sums, then the scalar update in its own launch
     const bool p2p = dist && comm->p2p;
-    static const bool allow_fused = !( getenv("OB200_FUSED_HALO") && getenv("OB200_FUSED_HALO")[0] == '0' );
+    const bool allow_fused = !( getenv("OB200_FUSED_HALO") && getenv("OB200_FUSED_HALO")[0] == '0' );
     const bool fused_halo = allow_fused && p2p && comm->nneigh > 0 && comm->route.p && spmv_halo_supported(A);
     const ob200_mailbox_layout ML = mailbox_layout(comm ? comm->nranks : 1, comm ? comm->cap : 1);
     auto finish = [&](int stage, int iter, int nred, const double *pa = nullptr, int nA = 0, const double *pb = nullptr, int nB = 0) -> int {

@@ -137,6 +137,22 @@ __global__ void csr_assemble_kernel(const int32_t *__restrict__ loc, const doubl
     }
 }
 
+// CompCol::assemble(rloc, cloc, mat) (compcol.C:301-336): only the rloc x cloc entries are touched
+__global__ void csr_assemble_rect_kernel(const int32_t *__restrict__ rloc, const int32_t *__restrict__ cloc, const double *__restrict__ mat,
+                                         int nr, int nc, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                         double *__restrict__ val, int *__restrict__ missing)
+{
+    for ( int t = blockIdx.x * blockDim.x + threadIdx.x; t < nr * nc; t += gridDim.x * blockDim.x ) {
+        const int i = t / nc, j = t - i * nc;
+        const int r = rloc[i], c = cloc[j];
+        if ( r > 0 && c > 0 ) {
+            const int p = find_slot(rowptr, colind, r - 1, c - 1);
+            if ( p < 0 ) atomicAdd(missing, 1);
+            else atomicAdd(val + p, mat[t]);
+        }
+    }
+}
+
 __global__ void scale_kernel(double *__restrict__ v, int64_t n, double s)
 {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
@@ -184,6 +200,19 @@ spmv_rowwarp_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32
 
 using namespace ob200;
 
+namespace ob200 {
+// SparseMtrx::timesT (compcol.C:146-163): y = A^T x.  Eight lanes per row scatter val * x[row] into y[col].
+__global__ void csr_times_t_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                   const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, stride = ( (int64_t) gridDim.x * blockDim.x ) >> 3;
+    const int sub = (int)( t & 7 );
+    for ( int64_t r = t >> 3; r < neq; r += stride ) {
+        const double xr = x[r];
+        for ( int k = rowptr[r] + sub; k < rowptr[r + 1]; k += 8 ) atomicAdd(y + colind[k], val[k] * xr);
+    }
+}
+}
 void ob200_csr_touch(ob200_csr *A) { A->version++; }
 
 int ob200_csr_materialize(ob200_csr *A)
@@ -590,6 +619,32 @@ int ob200_csr_assemble(ob200_csr *A, int64_t nelem, int32_t nd, const int32_t *l
     return OB200_OK;
 }
 
+int ob200_csr_assemble_rect(ob200_csr *A, int32_t nr, int32_t nc, const int32_t *rloc, const int32_t *cloc, const double *mat, int on_device)
+{
+    if ( A ) ob200::bind_stream(A->ctx);
+    OB_REQUIRE(A && rloc && cloc && mat, OB200_EINVAL, "csr_assemble_rect: null argument");
+    OB_REQUIRE(nr >= 0 && nc >= 0, OB200_EINVAL, "csr_assemble_rect: negative size");
+    if ( nr == 0 || nc == 0 ) return OB200_OK;
+    ob200_context *ctx = A->ctx;
+    OB_CHECK( ob200_csr_materialize(A) );
+    Staged< int32_t > R, Cc;
+    Staged< double > M;
+    OB_CHECK( R.stage(ctx, rloc, nr, on_device) );
+    OB_CHECK( Cc.stage(ctx, cloc, nc, on_device) );
+    OB_CHECK( M.stage(ctx, mat, (int64_t) nr * nc, on_device) );
+    DevBuf< int > missing;
+    OB_CHECK( missing.alloc(1) );
+    OB_CUDA( cudaMemsetAsync(missing.p, 0, sizeof( int ), ctx->stream) );
+    OB_LAUNCH(ctx, csr_assemble_rect_kernel, ctx->shape.grid((int64_t) nr * nc, 256, 8), 256, 0, R.d, Cc.d, M.d, nr, nc, A->rowptr.p,
+              A->colind.p, A->val.p, missing.p);
+    int h = 0;
+    OB_CUDA( cudaMemcpyAsync(&h, missing.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    A->version++;
+    OB_REQUIRE(h == 0, OB200_ESTRUCT, "csr_assemble_rect: couldn't find %d entries in the sparse structure", h);
+    return OB200_OK;
+}
+
 int ob200_csr_times(ob200_csr *A, const double *x, double *y, int on_device)
 {
     if ( A ) ob200::bind_stream(A->ctx);
@@ -599,6 +654,23 @@ int ob200_csr_times(ob200_csr *A, const double *x, double *y, int on_device)
     OB_CHECK( X.stage(A->ctx, x, A->neq, on_device) );
     OB_CHECK( Y.stage(A->ctx, y, A->neq, on_device) );
     OB_CHECK( spmv(A, X.d, Y.d) );
+    return Y.finish(A->ctx);
+}
+
+int ob200_csr_times_t(ob200_csr *A, const double *x, double *y, int on_device)
+{
+    if ( A ) ob200::bind_stream(A->ctx);
+    OB_REQUIRE(A && ( A->neq == 0 || ( x && y ) ), OB200_EINVAL, "csr_times_t: null argument");
+    Staged< double > X;
+    StagedOut< double > Y;
+    OB_CHECK( X.stage(A->ctx, x, A->neq, on_device) );
+    OB_CHECK( Y.stage(A->ctx, y, A->neq, on_device) );
+    OB_CHECK( ob200_csr_materialize(A) );
+    if ( A->neq ) {
+        OB_CUDA( cudaMemsetAsync(Y.d, 0, sizeof( double ) * (size_t) A->neq, A->ctx->stream) );
+        OB_LAUNCH(A->ctx, ob200::csr_times_t_kernel, A->ctx->shape.grid((int64_t) A->neq * 8, 256, 8), 256, 0, A->neq, A->rowptr.p,
+                  A->colind.p, A->val.p, X.d, Y.d);
+    }
     return Y.finish(A->ctx);
 }
 
@@ -614,7 +686,7 @@ int ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value)
     OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
     int n = rp[1] - rp[0];
     *value = 0.0;
-    if ( n <= 0 ) return OB200_OK;
+    if ( n <= 0 ) return 1;
     std::vector< int32_t > cols(n);
     OB_CUDA( cudaMemcpyAsync(cols.data(), A->colind.p + rp[0], sizeof( int32_t ) * n, cudaMemcpyDeviceToHost, A->ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
@@ -622,9 +694,9 @@ int ob200_csr_at(ob200_csr *A, int32_t i, int32_t j, double *value)
         if ( cols[k] == j - 1 ) {
             OB_CUDA( cudaMemcpyAsync(value, A->val.p + rp[0] + k, sizeof( double ), cudaMemcpyDeviceToHost, A->ctx->stream) );
             OB_CUDA( cudaStreamSynchronize(A->ctx->stream) );
-            break;
+            return OB200_OK;
         }
-    return OB200_OK;
+    return 1;          // in bounds but not in the sparse structure: value 0 (CompCol::at const, compcol.C:392-399)
 }
 
 } // extern "C"

@@ -200,6 +200,26 @@ __device__ __forceinline__ double tet_setup(const ElemSetView &S, int64_t e, dou
     return fabs(det) * ( 1.0 / 6.0 );     // gaussintegrationrule.C:500-507 weight 1/6
 }
 
+// FEI3dTetLin::evaldNdx raises OOFEM_ERROR("negative volume") for detJ <= 0 (fei3dtetlin.C:145-147): checked for the whole
+// set when it is created; bad[0] = number of such elements, bad[1] = the first one (smallest number)
+__global__ void tet_volume_check_kernel(ElemSetView S, int64_t nelem, int *__restrict__ bad)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride ) {
+        double g[4][3], c[12];
+#pragma unroll
+        for ( int a = 0; a < 4; a++ ) {
+            const int node = S.conn[e * 4 + a] - 1;
+#pragma unroll
+            for ( int j = 0; j < 3; j++ ) c[3 * a + j] = S.coords[(int64_t) node * 3 + j];
+        }
+        if ( !( tet_dNdx(c, g) > 0.0 ) ) {
+            atomicAdd(bad, 1);
+            atomicMin(bad + 1, (int) min(e, (int64_t) 0x7FFFFFFF));
+        }
+    }
+}
+
 template< int MODE >
 __global__ void __launch_bounds__(128)
 ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot,
@@ -501,8 +521,27 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
             S->all_isole = false;
         }
     }
+    if ( etype == OB200_LTRSPACE && nelem > 0 ) {
+        DevBuf< int > bad;
+        int hb[2] = { 0, 0x7FFFFFFF };
+        if ( ( rc = bad.alloc(2) ) < 0 ) { delete S; return rc; }
+        cudaMemcpyAsync(bad.p, hb, sizeof( hb ), cudaMemcpyHostToDevice, ctx->stream);
+        tet_volume_check_kernel<<< ctx->shape.grid(nelem, 128, 8), 128, 0, ctx->stream >>>(S->view(), nelem, bad.p);
+        ctx->launches++;
+        if ( cudaMemcpyAsync(hb, bad.p, sizeof( hb ), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+             cudaStreamSynchronize(ctx->stream) != cudaSuccess ) {
+            set_error("elemset_create: volume check failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            delete S;
+            return OB200_ECUDA;
+        }
+        if ( hb[0] > 0 ) {
+            set_error("FEI3dTetLin::evaldNdx: negative volume (%d LTRSpace elements, first: element %d)", hb[0], hb[1] + 1);
+            delete S;
+            return OB200_EINVAL;
+        }
+    }
     // the schedule of the last destroyed set is adopted if it was built from identical arrays (OB200_SCHED_CACHE=0 disables)
-    static const bool use_cache = !( getenv("OB200_SCHED_CACHE") && !strcmp(getenv("OB200_SCHED_CACHE"), "0") );
+    const bool use_cache = !( getenv("OB200_SCHED_CACHE") && !strcmp(getenv("OB200_SCHED_CACHE"), "0") );
     bool adopted = false;
     if ( use_cache && nelem > 0 ) {
         if ( ( rc = elemset_await_loc(S) ) < 0 ) { delete S; return rc; }

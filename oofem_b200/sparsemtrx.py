@@ -59,6 +59,19 @@ class CudaCSR:
         check(lib().ob200_csr_times(self.h, ptr(x), ptr(answer), on_device(x)))
         return answer
 
+    def timesT(self, x, answer=None):                       # SparseMtrx::timesT (compcol.C:146-163)
+        n = self.giveNumberOfRows()
+        if int(np.prod(x.shape)) != n:
+            raise capi.OofemB200Error(capi.EINVAL, "incompatible dimensions")
+        if answer is None:
+            if isinstance(x, np.ndarray):
+                answer = np.zeros(n)
+            else:
+                import torch
+                answer = torch.zeros(n, dtype=torch.float64, device=x.device)
+        check(lib().ob200_csr_times_t(self.h, ptr(x), ptr(answer), on_device(x)))
+        return answer
+
     def times_scalar(self, s: float):                       # SparseMtrx::times(double) (compcol.C:159-164)
         check(lib().ob200_csr_scale(self.h, float(s)))
 
@@ -69,6 +82,10 @@ class CudaCSR:
         v = C.c_double(0.0)
         check(lib().ob200_csr_at(self.h, i, j, C.byref(v)))
         return v.value
+
+    def isAllocatedAt(self, i: int, j: int) -> bool:         # SparseMtrx::isAllocatedAt: (i,j) is in the sparse structure
+        v = C.c_double(0.0)
+        return lib().ob200_csr_at(self.h, i, j, C.byref(v)) == 0
 
     def giveNumberOfRows(self) -> int:
         return lib().ob200_csr_rows(self.h)
@@ -95,10 +112,17 @@ class CudaCSR:
         check(lib().ob200_csr_get_structure(self.h, ptr(rp), ptr(ci), 0))
         return rp, ci[:self.giveNumberOfNonzeros()]
 
-    def values(self):
-        v = np.zeros(max(self.giveNumberOfNonzeros(), 1))
+    def values(self, device: bool = False):
+        """val[nnz]: numpy array, or (device=True) a torch tensor on the context's GPU (device-to-device copy)."""
+        n = self.giveNumberOfNonzeros()
+        if device:
+            import torch
+            v = torch.zeros(max(n, 1), dtype=torch.float64, device=torch.device("cuda", self.ctx.device))
+            check(lib().ob200_csr_get_values(self.h, ptr(v), 1))
+            return v[:n]
+        v = np.zeros(max(n, 1))
         check(lib().ob200_csr_get_values(self.h, ptr(v), 0))
-        return v[:self.giveNumberOfNonzeros()]
+        return v[:n]
 
     def set_values(self, v):
         if isinstance(v, np.ndarray):

@@ -115,12 +115,7 @@ void CudaCSR :: flush() const
         double d = c.second.cur - c.second.seen;
         if ( d != 0.0 ) {
             int32_t l [ 2 ] = { c.first.first, c.first.second };
-            if ( l [ 0 ] == l [ 1 ] ) {
-                CudaContext :: check(ob200_csr_assemble(A, 1, 1, l, & d, 0), "CudaCSR::at");
-            } else {
-                double m [ 4 ] = { 0., d, 0., 0. };                 // row-major 2 x 2: only (i, j)
-                CudaContext :: check(ob200_csr_assemble(A, 1, 2, l, m, 0), "CudaCSR::at");
-            }
+            CudaContext :: check(ob200_csr_assemble_rect(A, 1, 1, l, l + 1, & d, 0), "CudaCSR::at");
         }
     }
     cells.clear();
@@ -157,21 +152,24 @@ int CudaCSR :: assemble(const IntArray &loc, const FloatMatrix &mat)
 
 int CudaCSR :: assemble(const IntArray &rloc, const IntArray &cloc, const FloatMatrix &mat)
 {
-    // rectangular contribution: embedded into the square block (rloc, cloc) x (rloc, cloc)
+    // rectangular contribution: only rloc x cloc is touched, like CompCol::assemble(rloc, cloc, mat) (compcol.C:301-336)
     int nr = rloc.giveSize(), nc = cloc.giveSize();
     if ( nr != mat.giveNumberOfRows() || nc != mat.giveNumberOfColumns() ) {
         OOFEM_ERROR("dimension of 'k' and 'loc' mismatch");
     }
-    IntArray loc(rloc);
-    loc.followedBy(cloc);
-    // only the (row half) x (column half) block carries values
-    FloatMatrix sq(nr + nc, nr + nc);
-    for ( int i = 0; i < nr; i++ ) {
+    if ( nr == 0 || nc == 0 ) {
+        return 1;
+    }
+    this->flush();
+    std :: vector< double >m( ( size_t ) nr * nc );
+    for ( int i = 0; i < nr; i++ ) {         // FloatMatrix is column-major, the C ABI row-major
         for ( int j = 0; j < nc; j++ ) {
-            sq(i, nr + j) = mat(i, j);
+            m [ ( size_t ) i * nc + j ] = mat(i, j);
         }
     }
-    return this->assemble(loc, sq);
+    CudaContext :: check(ob200_csr_assemble_rect(A, nr, nc, rloc.givePointer(), cloc.givePointer(), m.data(), 0), "CudaCSR::assemble");
+    this->version++;
+    return 1;
 }
 
 void CudaCSR :: times(const FloatArray &x, FloatArray &answer) const
@@ -188,8 +186,14 @@ void CudaCSR :: times(const FloatArray &x, FloatArray &answer) const
 
 void CudaCSR :: timesT(const FloatArray &x, FloatArray &answer) const
 {
-    // only exact for a symmetric matrix; the structural tangents on this path are
-    OOFEM_ERROR("Not implemented");
+    if ( x.giveSize() != nRows ) {
+        OOFEM_ERROR("Error in CompCol -- incompatible dimensions");           // compcol.C:148-150
+    }
+    this->flush();
+    answer.resize(nColumns);
+    if ( nRows ) {
+        CudaContext :: check(ob200_csr_times_t(A, x.givePointer(), answer.givePointer(), 0), "CudaCSR::timesT");
+    }
 }
 
 void CudaCSR :: times(double x)
@@ -233,7 +237,7 @@ double &CudaCSR :: at(int i, int j)
         }
         double v = 0.;
         int rc = ob200_csr_at(A, i, j, & v);
-        if ( rc < 0 ) {
+        if ( rc != OB200_OK ) {               // out of bounds, or not in the sparse structure: CompCol::at raises for both
             OOFEM_ERROR("Array accessing exception -- (%d,%d) out of bounds", i, j);    // compcol.C:372
         }
         it = cells.insert({ key, Cell { v, v } }).first;
