@@ -134,7 +134,7 @@ int64_t ob200_elemset_size(const ob200_elemset *S);
 int  ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device);
 /* element internal force vectors fe [nelem][nd] for nodal displacements u [nnode][3]
  * (giveInternalForcesVector, useUpdatedGpRecord = 0); updates the temp material state.
- * gp_strain / gp_stress [nelem*ngp][6] optional (NULL to skip). */
+ * fe and gp_strain / gp_stress [nelem*ngp][6] are optional (NULL to skip). */
 int  ob200_elemset_internal_forces(ob200_elemset *S, const double *u, double *fe,
                                    double *gp_strain, double *gp_stress, int on_device);
 /* bind the set to a matrix: precomputes the element -> CSR slot map */

@@ -608,14 +608,14 @@ int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
 int ob200_elemset_internal_forces(ob200_elemset *S, const double *u, double *fe, double *gp_strain, double *gp_stress, int on_device)
 {
     if ( S ) ob200::bind_stream(S->ctx);
-    OB_REQUIRE(S && u && fe, OB200_EINVAL, "elemset_internal_forces: null argument");
+    OB_REQUIRE(S && u, OB200_EINVAL, "elemset_internal_forces: null argument");
     Staged< double > du;
     StagedOut< double > of, oe, os;
     OB_CHECK( du.stage(S->ctx, u, S->nnode * 3, on_device) );
-    OB_CHECK( of.stage(S->ctx, fe, S->nelem * S->nd, on_device) );
+    if ( fe ) OB_CHECK( of.stage(S->ctx, fe, S->nelem * S->nd, on_device) );
     if ( gp_strain ) OB_CHECK( oe.stage(S->ctx, gp_strain, S->nelem * S->ngp * 6, on_device) );
     if ( gp_stress ) OB_CHECK( os.stage(S->ctx, gp_stress, S->nelem * S->ngp * 6, on_device) );
-    OB_CHECK( launch_internal_forces(S, du.d, of.d, nullptr, gp_strain ? oe.d : nullptr, gp_stress ? os.d : nullptr) );
+    OB_CHECK( launch_internal_forces(S, du.d, fe ? of.d : nullptr, nullptr, gp_strain ? oe.d : nullptr, gp_stress ? os.d : nullptr) );
     OB_CHECK( of.finish(S->ctx) );
     OB_CHECK( oe.finish(S->ctx) );
     return os.finish(S->ctx);

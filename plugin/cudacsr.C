@@ -20,10 +20,15 @@
 #include "sm/Elements/3D/lspace.h"
 #include "sm/Elements/3D/ltrspace.h"
 #include "sm/Materials/isolinearelasticmaterial.h"
+#include "sm/Materials/misesmat.h"
+#include "sm/Materials/structuralms.h"
+#include "dof.h"
+#include "dofiditem.h"
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <typeinfo>
 
 namespace oofem {
@@ -39,18 +44,7 @@ CudaCSR :: CudaCSR(int n) : SparseMtrx(n, n)
 
 CudaCSR :: ~CudaCSR()
 {
-    this->dropElementSet();
     ob200_csr_destroy(A);
-}
-
-void CudaCSR :: dropElementSet()
-{
-    if ( set ) {
-        ob200_elemset_destroy(set);
-        set = nullptr;
-    }
-    setDomain = nullptr;
-    setTried = false;
 }
 
 int CudaCSR :: buildInternalStructure(EngngModel *eModel, int di, const UnknownNumberingScheme &s)
@@ -94,7 +88,7 @@ int CudaCSR :: buildInternalStructure(EngngModel *eModel, int di, const UnknownN
     pendMat.clear();
     pendCount = 0;
     cells.clear();
-    this->dropElementSet();
+    batchedUsed = false;
     CudaContext :: check(ob200_csr_build_structure(A, neq, ( int64_t ) locs.size(), std :: max(width, 1), flat.data(), 0),
                          "CudaCSR::buildInternalStructure");
     nRows = nColumns = neq;
@@ -278,134 +272,343 @@ void CudaCSR :: toFloatMatrix(FloatMatrix &answer) const
 void CudaCSR :: printStatistics() const
 {
     OOFEM_LOG_INFO("CudaCSR info: neq is %d, nwk is %ld, batched assembly %s\n", nRows, ( long ) ob200_csr_nnz(A),
-                   set ? "on" : "off");
+                   batchedUsed ? "on" : "off");
 }
 
 // ---- batched element-evaluation hook ------------------------------------------------------------
+//
+// One resident element set per domain (ob200_elemset: connectivity, coordinates, location arrays, material table, MisesMat
+// state in HBM).  Accepted: a domain made of plain LSpace or plain LTRSpace elements (small strain, default integration
+// rule, no local coordinate systems) whose materials are IsotropicLinearElasticMaterial or MisesMat (hType 0).  Anything
+// else keeps the reference's host loops.
 
-bool CudaCSR :: buildElementSet(EngngModel *eModel, const UnknownNumberingScheme &s, Domain *domain)
-{
-    // Accepts a domain made of plain LSpace or plain LTRSpace elements (small strain, default
-    // integration rule) with IsotropicLinearElasticMaterial and nodes without local coordinate
-    // systems.  Anything else keeps the reference's host loop.
-    int nelem = domain->giveNumberOfElements();
-    int nnode = domain->giveNumberOfDofManagers();
-    if ( nelem == 0 || nnode == 0 ) {
-        return false;
+namespace {
+// protected members the hook has to look at (the classes have no accessors for them)
+struct TangentPeek : public TangentAssembler {
+    using TangentAssembler :: rmode;
+};
+struct MisesPeek : public MisesMat {
+    using MisesMat :: hType;
+    using MisesMat :: linearElasticMaterial;
+    using MisesMat :: omega_crit;
+    using MisesMat :: a;
+};
+
+struct BatchedDomain {
+    ob200_elemset *set = nullptr;
+    Domain *domain = nullptr;
+    int domainVersion = -1, neq = -1, etype = 0, nen = 0, ngp = 0, nelem = 0, nnode = 0;
+    bool tried = false, hasMises = false;
+    std :: vector< double >matparams;              // the table the set was created with
+    std :: vector< Material * >mats;               // row -> material
+    std :: vector< double >u;                      // scratch: nodal displacements
+
+    void drop()
+    {
+        if ( set ) {
+            ob200_elemset_destroy(set);
+            set = nullptr;
+        }
+        tried = false;
     }
-    int etype = 0, nen = 0;
-    const char *cn = domain->giveElement(1)->giveClassName();
-    if ( !std :: strcmp(cn, "LSpace") ) {
-        etype = OB200_LSPACE;
-        nen = 8;
-    } else if ( !std :: strcmp(cn, "LTRSpace") ) {
-        etype = OB200_LTRSPACE;
-        nen = 4;
-    } else {
-        return false;
-    }
-    const int ngp = etype == OB200_LSPACE ? 8 : 1;
-    std :: vector< int32_t >conn( ( size_t ) nelem * nen), matid(nelem), loc( ( size_t ) nelem * nen * 3);
-    std :: map< int, int >matIndex;                  // material number -> row of the parameter table
-    std :: vector< double >matparams;
-    IntArray l, ids;
-    FloatMatrix R;
-    for ( int e = 1; e <= nelem; e++ ) {
-        Element *elem = domain->giveElement(e);
-        if ( std :: strcmp(elem->giveClassName(), cn) ) {
-            return false;
+
+    static bool materialRow(Material *m, GaussPoint *gp, TimeStep *tStep, double row [ OB200_MATPARAM_STRIDE ])
+    {
+        for ( int k = 0; k < OB200_MATPARAM_STRIDE; k++ ) {
+            row [ k ] = 0.;
         }
-        NLStructuralElement *se = dynamic_cast< NLStructuralElement * >( elem );
-        if ( !se || se->giveGeometryMode() != 0 || elem->giveRotationMatrix(R) ) {
-            return false;
-        }
-        IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
-        if ( !iRule || iRule->giveNumberOfIntegrationPoints() != ngp || elem->giveNumberOfIntegrationRules() != 1 ) {
-            return false;
-        }
-        const IntArray &dm = elem->giveDofManArray();
-        if ( dm.giveSize() != nen ) {
-            return false;
-        }
-        for ( int k = 0; k < nen; k++ ) {
-            conn [ ( size_t ) ( e - 1 ) * nen + k ] = dm [ k ];
-        }
-        elem->giveLocationArray(l, s, & ids);
-        if ( l.giveSize() != 3 * nen ) {
-            return false;
-        }
-        for ( int k = 0; k < 3 * nen; k++ ) {
-            if ( ids [ k ] != D_u + k % 3 ) {
-                return false;
-            }
-            loc [ ( size_t ) ( e - 1 ) * nen * 3 + k ] = l [ k ];
-        }
-        // the material comes through the cross section (Structural3DElement::computeConstitutiveMatrixAt,
-        // structural3delement.C:99-103); one material per element on this path
-        Material *m = elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(0) );
-        for ( int g = 1; g < ngp; g++ ) {
-            if ( elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(g) ) != m ) {
-                return false;
-            }
-        }
-        auto found = matIndex.find( m->giveNumber() );
-        if ( found == matIndex.end() ) {
-            if ( std :: strcmp(m->giveClassName(), "IsotropicLinearElasticMaterial") ) {
-                return false;
-            }
+        if ( !std :: strcmp(m->giveClassName(), "IsotropicLinearElasticMaterial") ) {
             auto *iso = static_cast< IsotropicLinearElasticMaterial * >( m );
-            found = matIndex.insert({ m->giveNumber(), ( int ) matIndex.size() }).first;
-            double row [ OB200_MATPARAM_STRIDE ] = { ( double ) OB200_MAT_ISOLE, iso->giveYoungsModulus(), iso->givePoissonsRatio(), 0., 0., 0., 0., 0. };
-            matparams.insert(matparams.end(), row, row + OB200_MATPARAM_STRIDE);
+            row [ 0 ] = OB200_MAT_ISOLE;
+            row [ 1 ] = iso->giveYoungsModulus();
+            row [ 2 ] = iso->givePoissonsRatio();
+            return true;
         }
-        matid [ e - 1 ] = found->second;
-    }
-    std :: vector< double >coords( ( size_t ) nnode * 3, 0.);
-    for ( int n = 1; n <= nnode; n++ ) {
-        DofManager *dman = domain->giveDofManager(n);
-        const FloatArray &c = dman->giveCoordinates();
-        for ( int k = 0; k < std :: min(3, c.giveSize()); k++ ) {
-            coords [ ( size_t ) ( n - 1 ) * 3 + k ] = c [ k ];
+        if ( !std :: strcmp(m->giveClassName(), "MisesMat") ) {
+            auto *mm = static_cast< MisesMat * >( m );
+            const MisesPeek *pk = static_cast< const MisesPeek * >( mm );
+            if ( pk->hType != 0 ) {
+                return false;                       // user-defined hardening curve: host loop
+            }
+            row [ 0 ] = OB200_MAT_MISES;
+            row [ 1 ] = pk->linearElasticMaterial.giveYoungsModulus();
+            row [ 2 ] = pk->linearElasticMaterial.givePoissonsRatio();
+            row [ 3 ] = mm->computeYieldStress(0., gp, tStep);          // sig0 (a ScalarFunction: re-read every call)
+            row [ 4 ] = mm->computeYieldStressPrime(0.);                // H
+            row [ 5 ] = pk->omega_crit;
+            row [ 6 ] = pk->a;
+            return true;
         }
+        return false;
     }
-    int neq = eModel->giveNumberOfDomainEquations(domain->giveNumber(), s);
-    CudaContext :: check(ob200_elemset_create(CudaContext :: get(), etype, nnode, coords.data(), nelem, conn.data(), matid.data(),
-                                              ( int32_t ) matIndex.size(), matparams.data(), loc.data(), neq, 0, & set),
-                         "CudaCSR: element set");
-    CudaContext :: check(ob200_elemset_bind(set, A), "CudaCSR: element set bind");
-    setDomain = domain;
-    setDomainVersion = domain->giveSerialNumber();
-    return true;
+
+    bool build(EngngModel *eModel, TimeStep *tStep, const UnknownNumberingScheme &s, Domain *d)
+    {
+        nelem = d->giveNumberOfElements();
+        nnode = d->giveNumberOfDofManagers();
+        if ( nelem == 0 || nnode == 0 ) {
+            return false;
+        }
+        const char *cn = d->giveElement(1)->giveClassName();
+        if ( !std :: strcmp(cn, "LSpace") ) {
+            etype = OB200_LSPACE;
+            nen = 8;
+        } else if ( !std :: strcmp(cn, "LTRSpace") ) {
+            etype = OB200_LTRSPACE;
+            nen = 4;
+        } else {
+            return false;
+        }
+        ngp = etype == OB200_LSPACE ? 8 : 1;
+        std :: vector< int32_t >conn( ( size_t ) nelem * nen), matid(nelem), loc( ( size_t ) nelem * nen * 3);
+        std :: map< int, int >matIndex;                  // material number -> row of the parameter table
+        matparams.clear();
+        mats.clear();
+        hasMises = false;
+        IntArray l, ids;
+        FloatMatrix R;
+        for ( int e = 1; e <= nelem; e++ ) {
+            Element *elem = d->giveElement(e);
+            if ( std :: strcmp(elem->giveClassName(), cn) ) {
+                return false;
+            }
+            NLStructuralElement *se = dynamic_cast< NLStructuralElement * >( elem );
+            if ( !se || se->giveGeometryMode() != 0 || elem->giveRotationMatrix(R) ) {
+                return false;
+            }
+            IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
+            if ( !iRule || iRule->giveNumberOfIntegrationPoints() != ngp || elem->giveNumberOfIntegrationRules() != 1 ) {
+                return false;
+            }
+            const IntArray &dm = elem->giveDofManArray();
+            if ( dm.giveSize() != nen ) {
+                return false;
+            }
+            for ( int k = 0; k < nen; k++ ) {
+                conn [ ( size_t ) ( e - 1 ) * nen + k ] = dm [ k ];
+            }
+            elem->giveLocationArray(l, s, & ids);
+            if ( l.giveSize() != 3 * nen ) {
+                return false;
+            }
+            for ( int k = 0; k < 3 * nen; k++ ) {
+                if ( ids [ k ] != D_u + k % 3 ) {
+                    return false;
+                }
+                loc [ ( size_t ) ( e - 1 ) * nen * 3 + k ] = l [ k ];
+            }
+            // the material comes through the cross section (Structural3DElement::computeConstitutiveMatrixAt,
+            // structural3delement.C:99-103); one material per element on this path
+            Material *m = elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(0) );
+            for ( int g = 1; g < ngp; g++ ) {
+                if ( elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(g) ) != m ) {
+                    return false;
+                }
+            }
+            auto found = matIndex.find( m->giveNumber() );
+            if ( found == matIndex.end() ) {
+                double row [ OB200_MATPARAM_STRIDE ];
+                if ( !materialRow(m, iRule->getIntegrationPoint(0), tStep, row) ) {
+                    return false;
+                }
+                hasMises = hasMises || row [ 0 ] == OB200_MAT_MISES;
+                found = matIndex.insert({ m->giveNumber(), ( int ) matIndex.size() }).first;
+                matparams.insert(matparams.end(), row, row + OB200_MATPARAM_STRIDE);
+                mats.push_back(m);
+            }
+            matid [ e - 1 ] = found->second;
+        }
+        std :: vector< double >coords( ( size_t ) nnode * 3, 0.);
+        for ( int n = 1; n <= nnode; n++ ) {
+            const FloatArray &c = d->giveDofManager(n)->giveCoordinates();
+            for ( int k = 0; k < std :: min(3, c.giveSize()); k++ ) {
+                coords [ ( size_t ) ( n - 1 ) * 3 + k ] = c [ k ];
+            }
+        }
+        neq = eModel->giveNumberOfDomainEquations(d->giveNumber(), s);
+        CudaContext :: check(ob200_elemset_create(CudaContext :: get(), etype, nnode, coords.data(), nelem, conn.data(), matid.data(),
+                                                  ( int32_t ) matIndex.size(), matparams.data(), loc.data(), neq, 0, & set),
+                             "CudaCSR: element set");
+        domain = d;
+        domainVersion = d->giveSerialNumber();
+        return true;
+    }
+
+    /// The set for this domain and numbering, built on first use; nullptr if the domain is not of the accepted kind (or a
+    /// condition the host loops test per element and step does not hold now).
+    ob200_elemset *get(EngngModel *eModel, TimeStep *tStep, const UnknownNumberingScheme &s, Domain *d)
+    {
+        if ( std :: getenv("OOFEM_B200_NO_BATCH") ) {
+            return nullptr;
+        }
+        if ( set && ( domain != d || domainVersion != d->giveSerialNumber() ||
+                      neq != eModel->giveNumberOfDomainEquations(d->giveNumber(), s) ) ) {
+            this->drop();
+        }
+        if ( !set ) {
+            if ( tried ) {
+                return nullptr;
+            }
+            tried = true;
+            if ( !this->build(eModel, tStep, s, d) ) {
+                return nullptr;
+            }
+        }
+        // the conditions the host loops test per element and step (engngm.C:909-911, 1386-1392)
+        for ( auto &elem : d->giveElements() ) {
+            if ( elem->giveParallelMode() == Element_remote || !elem->isActivated(tStep) || !eModel->isElementActivated( elem.get() ) ) {
+                return nullptr;
+            }
+        }
+        // material parameters that may depend on time (MisesMat sig0 is a ScalarFunction): a change sends the job back to the host
+        for ( std :: size_t m = 0; m < mats.size(); m++ ) {
+            double row [ OB200_MATPARAM_STRIDE ];
+            GaussPoint *gp = d->giveElement(1)->giveDefaultIntegrationRulePtr()->getIntegrationPoint(0);
+            if ( !materialRow(mats [ m ], gp, tStep, row) || std :: memcmp(row, & matparams [ m * OB200_MATPARAM_STRIDE ], sizeof( row ) ) ) {
+                return nullptr;
+            }
+        }
+        return set;
+    }
+
+    /// nodal values of (D_u, D_v, D_w) in the given mode: what StructuralElement::computeVectorOf collects per element
+    const double *displacements(ValueModeType mode, TimeStep *tStep)
+    {
+        u.assign( ( size_t ) nnode * 3, 0.);
+        for ( int n = 1; n <= nnode; n++ ) {
+            DofManager *dman = domain->giveDofManager(n);
+            for ( int k = 0; k < 3; k++ ) {
+                auto it = dman->findDofWithDofId( ( DofIDItem ) ( D_u + k ) );
+                if ( it != dman->end() ) {
+                    u [ ( size_t ) ( n - 1 ) * 3 + k ] = ( * it )->giveUnknown(mode, tStep);
+                }
+            }
+        }
+        return u.data();
+    }
+};
+
+std :: map< Domain *, BatchedDomain > &batchedDomains()
+{
+    static std :: map< Domain *, BatchedDomain >m;
+    return m;
 }
+} // namespace
+
+int CudaCSR :: batchedVectorCalls = 0;
+int CudaCSR :: batchedUpdateCalls = 0;
 
 bool CudaCSR :: assembleBatched(EngngModel *eModel, TimeStep *tStep, const MatrixAssembler &ma,
                                 const UnknownNumberingScheme &s, Domain *domain)
 {
-    // tangent stiffness only (for the linear elastic material every MatResponseMode gives the same D)
-    if ( typeid( ma ) != typeid( TangentAssembler ) || std :: getenv("OOFEM_B200_NO_BATCH") ) {
+    if ( typeid( ma ) != typeid( TangentAssembler ) ) {
         return false;
     }
-    if ( set && ( setDomain != domain || setDomainVersion != domain->giveSerialNumber() ) ) {
-        this->dropElementSet();
-    }
+    BatchedDomain &bd = batchedDomains() [ domain ];
+    ob200_elemset *set = bd.get(eModel, tStep, s, domain);
     if ( !set ) {
-        if ( setTried ) {
-            return false;
-        }
-        setTried = true;
-        if ( !this->buildElementSet(eModel, s, domain) ) {
-            return false;
-        }
+        return false;
     }
-    // the conditions the host loop tests per element and step (engngm.C:909-911)
-    for ( auto &elem : domain->giveElements() ) {
-        if ( elem->giveParallelMode() == Element_remote || !elem->isActivated(tStep) || !eModel->isElementActivated( elem.get() ) ) {
-            return false;
-        }
+    // MisesMat::give3dMaterialStiffnessMatrix answers the elastic matrix for every mode but TangentStiffness
+    // (misesmat.C:496-503); the kernels evaluate the algorithmic tangent
+    if ( bd.hasMises && static_cast< const TangentPeek & >( static_cast< const TangentAssembler & >( ma ) ).rmode != TangentStiffness ) {
+        return false;
     }
     this->flush();
     CudaContext :: check(ob200_elemset_assemble_stiffness(set, A), "CudaCSR::assembleBatched");
     this->version++;
+    if ( !batchedUsed ) {
+        OOFEM_LOG_INFO("CudaCSR: batched tangent assembly on the GPU (%d elements)\n", bd.nelem);
+    }
+    batchedUsed = true;
     return true;
+}
+
+bool batchedAssembleVector(EngngModel *eModel, FloatArray &answer, TimeStep *tStep, const VectorAssembler &va, ValueModeType mode,
+                           const UnknownNumberingScheme &s, Domain *domain, FloatArray *eNorms)
+{
+    // internal forces of the total state only: InternalForceAssembler::vectorFromElement asks the element for
+    // InternalForcesVector (StructuralElement::giveInternalForcesVector, useUpdatedGpRecord = 0)
+    if ( typeid( va ) != typeid( InternalForceAssembler ) || mode != VM_Total ) {
+        return false;
+    }
+    auto it = batchedDomains().find(domain);
+    if ( it == batchedDomains().end() ) {
+        return false;                               // no cudacsr matrix on this domain: not our job
+    }
+    BatchedDomain &bd = it->second;
+    ob200_elemset *set = bd.get(eModel, tStep, s, domain);
+    if ( !set || answer.giveSize() != bd.neq ) {
+        return false;
+    }
+    double ebe [ 3 ] = { 0., 0., 0. };
+    CudaContext :: check(ob200_elemset_assemble_internal_forces(set, bd.displacements(mode, tStep), answer.givePointer(),
+                                                                eNorms ? ebe : nullptr, 0), "batched internal forces");
+    if ( eNorms ) {
+        for ( int k = 0; k < 3; k++ ) {
+            if ( D_u + k <= eNorms->giveSize() ) {
+                eNorms->at(D_u + k) += ebe [ k ];
+            }
+        }
+    }
+    if ( CudaCSR :: batchedVectorCalls++ == 0 ) {
+        OOFEM_LOG_INFO("CudaCSR: batched internal forces on the GPU (%d elements)\n", bd.nelem);
+    }
+    return true;
+}
+
+void batchedUpdate(EngngModel *eModel, TimeStep *tStep, Domain *domain)
+{
+    auto it = batchedDomains().find(domain);
+    if ( it == batchedDomains().end() || !it->second.set || CudaCSR :: batchedVectorCalls == 0 ) {
+        return;
+    }
+    BatchedDomain &bd = it->second;
+    // Strains, stresses (and the MisesMat variables) of the converged state into the temporary statuses of the host
+    // elements: Element::updateYourself, which runs next, commits them (structuralelement.C:944, misesmat.C:672-690),
+    // and the output modules read them.  OOFEM_B200_NO_STATUS_SYNC=1 skips the copy (no element output then).
+    if ( !std :: getenv("OOFEM_B200_NO_STATUS_SYNC") ) {
+        const size_t ngpt = ( size_t ) bd.nelem * bd.ngp;
+        std :: vector< double >eps(ngpt * 6), sig(ngpt * 6), state;
+        CudaContext :: check(ob200_elemset_internal_forces(bd.set, bd.displacements(VM_Total, tStep), nullptr, eps.data(), sig.data(), 0),
+                             "batched update: strains and stresses");
+        if ( bd.hasMises ) {
+            state.resize(ngpt * OB200_MISES_STATE_DOUBLES);
+            CudaContext :: check(ob200_elemset_get_state(bd.set, state.data(), 0), "batched update: material state");
+        }
+        FloatArray v6(6);
+        for ( int e = 1; e <= bd.nelem; e++ ) {
+            Element *elem = domain->giveElement(e);
+            IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
+            for ( int g = 0; g < bd.ngp; g++ ) {
+                GaussPoint *gp = iRule->getIntegrationPoint(g);
+                Material *m = elem->giveCrossSection()->giveMaterial(gp);
+                auto *st = static_cast< StructuralMaterialStatus * >( m->giveStatus(gp) );
+                const size_t o = ( ( size_t ) ( e - 1 ) * bd.ngp + g );
+                for ( int k = 0; k < 6; k++ ) v6 [ k ] = eps [ o * 6 + k ];
+                st->letTempStrainVectorBe(v6);
+                for ( int k = 0; k < 6; k++ ) v6 [ k ] = sig [ o * 6 + k ];
+                st->letTempStressVectorBe(v6);
+                if ( bd.hasMises && !std :: strcmp(m->giveClassName(), "MisesMat") ) {
+                    // layout of ob200 MisesState: plStrain[6] kappa damage tempPlStrain[6] tempKappa tempDamage
+                    // trialStressDev[6] trialStressVol effStress[6]
+                    const double *q = & state [ o * OB200_MISES_STATE_DOUBLES ];
+                    auto *ms = static_cast< MisesMatStatus * >( st );
+                    for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 8 + k ];
+                    ms->letTempPlasticStrainBe(v6);
+                    ms->setTempCumulativePlasticStrain(q [ 14 ]);
+                    ms->setTempDamage(q [ 15 ]);
+                    for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 16 + k ];
+                    ms->letTrialStressDevBe(v6);
+                    ms->setTrialStressVol(q [ 22 ]);
+                    for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 23 + k ];
+                    ms->letTempEffectiveStressBe(v6);
+                }
+            }
+        }
+    }
+    // MaterialStatus::updateYourself for the resident state: temp -> committed
+    CudaContext :: check(ob200_elemset_commit(bd.set), "batched update: commit");
+    CudaCSR :: batchedUpdateCalls++;
 }
 } // namespace oofem

@@ -34,16 +34,11 @@ protected:
         double seen, cur;
     };
     mutable std :: map< std :: pair< int, int >, Cell >cells;
-    // batched element-evaluation hook: one resident element set per (domain, numbering)
-    ob200_elemset *set = nullptr;
-    Domain *setDomain = nullptr;
-    int setDomainVersion = -1;
-    bool setTried = false;
-    std :: vector< char >setNoRotation;
+    // batched element-evaluation hook: the resident element set belongs to the domain (BatchedDomain in cudacsr.C), every
+    // CudaCSR of that domain assembles from it
+    bool batchedUsed = false;
 
     void flush() const;                 // send pending contributions and write back modified cells
-    void dropElementSet();
-    bool buildElementSet(EngngModel *eModel, const UnknownNumberingScheme &s, Domain *domain);
 
 public:
     CudaCSR(int n = 0);
@@ -74,7 +69,9 @@ public:
     int64_t giveNumberOfNonzeros() const { return ob200_csr_nnz(A); }
     /// Structure as CompCol stores it (colptr / rowind of the symmetric pattern), for tests.
     void giveStructure(IntArray &rowptr, IntArray &colind) const;
-    bool usesBatchedAssembly() const { return set != nullptr; }
+    bool usesBatchedAssembly() const { return batchedUsed; }
+    /// how often the vector hook (internal forces) and the status update ran on the GPU (tests)
+    static int batchedVectorCalls, batchedUpdateCalls;
 };
 } // namespace oofem
 #endif

@@ -4,7 +4,7 @@
 //   rowptr/colind/val a CudaCSR built by buildInternalStructure + EngngModel::assemble (batched hook)
 //   val_hostloop      the same matrix assembled by the host loop into CudaCSR::assemble(loc, mat)
 //   spmv_x / spmv_y   CudaCSR::times on a fixed vector
-//   meta              [neq, nnode, nelem, batched hook used (0/1)]
+//   meta              [neq, nnode, nelem, batched matrix hook used (0/1), batched internal-force calls, batched status updates]
 // Record format as oracle/ref_dump.cpp: [int32 namelen][name][int32 dtype][int64 count][payload].
 //
 //   oofem_dump_cuda <input.in> <out.bin>
@@ -107,7 +107,8 @@ int main(int argc, char **argv)
     rec("colind", 0, (int64_t) civ.size(), civ.data());
     std::vector<double> v = values(A);
     rec("val", 1, (int64_t) v.size(), v.data());
-    std::vector<int32_t> meta = { neq, d->giveNumberOfDofManagers(), d->giveNumberOfElements(), A.usesBatchedAssembly() ? 1 : 0 };
+    std::vector<int32_t> meta = { neq, d->giveNumberOfDofManagers(), d->giveNumberOfElements(), A.usesBatchedAssembly() ? 1 : 0,
+                                  CudaCSR::batchedVectorCalls, CudaCSR::batchedUpdateCalls };
     rec("meta", 0, (int64_t) meta.size(), meta.data());
 
     FloatArray x(neq), y;

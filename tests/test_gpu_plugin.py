@@ -86,20 +86,32 @@ def test_plugin_linear_static_vs_reference_dump(name, tmp_path):
 
 @pytest.mark.parametrize("name", ["lspace_mises", "ltrspace_mises"])
 def test_plugin_newton_raphson_mises_vs_reference_dump(name, tmp_path):
-    """StaticStructural + NRSolver + MisesMat: the hook declines (not linear elastic), the reference's host
-    loop assembles every Newton tangent into cudacsr and cudacg solves it."""
+    """StaticStructural + NRSolver + MisesMat entirely through the hooks: every Newton tangent
+    (EngngModel::assemble), every internal-force vector with its element norms
+    (EngngModel::assembleVectorFromElements) and the status commit (EngngModel::updateYourself) run on the GPU;
+    the displacements match the unmodified reference to 1e-8."""
     need(DUMP)
     out = tmp_path / "dump.bin"
     r = subprocess.run([DUMP, cuda_input(name, tmp_path), str(out)], capture_output=True, text=True, cwd=tmp_path, timeout=900)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     d = read_dump(str(out))
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
-    assert d["meta"][3] == 0
+    assert d["meta"][3] == 1, "the batched matrix hook was not taken for MisesMat"
+    assert d["meta"][4] > 0, "the batched internal-force hook was not taken"
+    assert d["meta"][5] > 0, "the batched status update did not run"
     assert np.array_equal(d["rowptr"], g["colptr"]) and np.array_equal(d["colind"], g["rowind"])
     assert relerr(d["node_u"], g["node_u"]) < 1e-8
-    # (the tangent AFTER the converged step is not compared with the reference dump: with tempKappa == kappa up
-    # to round-off the loading/unloading branch of MisesMat::give3dMaterialStiffnessMatrix is decided by noise)
-    assert relerr(d["val_hostloop"], d["val"]) < 1e-14            # two host-loop assemblies of the same state agree
+    # (the tangent AFTER the converged step is not compared: with tempKappa == kappa up to round-off the
+    # loading/unloading branch of MisesMat::give3dMaterialStiffnessMatrix is decided by noise)
+
+    # the same input with the hooks switched off: host loops into cudacsr / cudacg
+    out2 = tmp_path / "dump_host.bin"
+    r = subprocess.run([DUMP, cuda_input(name, tmp_path), str(out2)], capture_output=True, text=True, cwd=tmp_path, timeout=900,
+                       env=dict(os.environ, OOFEM_B200_NO_BATCH="1"))
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    h = read_dump(str(out2))
+    assert h["meta"][3] == 0 and h["meta"][4] == 0
+    assert relerr(h["node_u"], g["node_u"]) < 1e-8
 
 
 def _numbers(fn):
@@ -123,3 +135,50 @@ def test_stock_executable_output_matches_reference_executable(tmp_path):
     ref = _numbers(tmp_path / (name + ".out"))
     assert ours.size == ref.size and ours.size > 500
     assert np.abs(ours - ref).max() <= 1e-6 * np.abs(ref).max()    # the .out prints ~5 significant digits
+
+
+def _element_output(fn):
+    """Numbers of the element records (strains, stresses, status variables per Gauss point) of an .out file."""
+    txt = open(fn).read()
+    txt = txt[txt.index("Element output:"):]
+    txt = txt[:txt.index("R E A C T I O N S") if "R E A C T I O N S" in txt else len(txt)]
+    return np.array([float(t) for t in re.findall(r"[-+]?\d+\.\d+e[-+]\d+", txt)])
+
+
+@pytest.mark.parametrize("name", ["lspace_mises"])
+def test_stock_executable_mises_output_matches_reference_executable(name, tmp_path):
+    """oofem_cuda -f on the MisesMat Newton-Raphson input: the .out file (displacements, and the Gauss-point strains,
+    stresses and plastic variables that the status update copies back from HBM) against the reference executable."""
+    need(EXE)
+    need(REF_EXE)
+    r = subprocess.run([EXE, "-f", cuda_input(name, tmp_path)], capture_output=True, text=True, cwd=tmp_path, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    os.rename(tmp_path / (name + ".out"), tmp_path / "cuda.out")
+    r = subprocess.run([REF_EXE, "-f", cuda_input(name, tmp_path, keep=True)], capture_output=True, text=True, cwd=tmp_path, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    ours, ref = _numbers(tmp_path / "cuda.out"), _numbers(tmp_path / (name + ".out"))
+    assert ours.size == ref.size and ours.size > 500
+    assert np.abs(ours - ref).max() <= 2e-5 * np.abs(ref).max()
+    eo, er = _element_output(tmp_path / "cuda.out"), _element_output(tmp_path / (name + ".out"))
+    assert eo.size == er.size and eo.size > 200 and np.abs(er).max() > 0
+    assert np.abs(eo - er).max() <= 2e-5 * np.abs(er).max()
+
+
+@pytest.mark.parametrize("name,hooked", [("deadweight02", True), ("patch300", True), ("Mises01", False)])
+def test_reference_own_tests_sm_through_the_plugin(name, hooked, tmp_path):
+    """The reference's own tests/sm inputs (copied unchanged to tests/golden/ref_sm) with `lstype 9 smtype 11`: their
+    #%BEGIN_CHECK% blocks are checked by the reference's errorcheck module inside the run (a mismatch is an OOFEM_ERROR and
+    a non-zero exit).  deadweight02 (LSpace, dead weight, nodes with single prescribed dofs) and patch300 (LTRSpace) take
+    the hooks; Mises01 is a truss1d model with both ends prescribed (no equation): host loops only."""
+    need(EXE)
+    lines = open(os.path.join(GOLDEN, "ref_sm", name + ".in")).read().splitlines()
+    k = next(i for i, l in enumerate(lines) if l.lower().startswith("staticstructural"))
+    lines[k] = lines[k].replace(" nmodules", " lstype 9 smtype 11 lstol 1e-14 lsiter 20000 lsprecond 1 nmodules")
+    fn = tmp_path / (name + ".in")
+    fn.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([EXE, "-f", str(fn)], capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0 and "Checking rules" in log and "Total 0 error(s)" in log, log[-3000:]
+    assert ("CudaCG" in log) == hooked          # Mises01 has no free dof: nothing to solve, the check values still hold
+    assert ("batched tangent assembly on the GPU" in log) == hooked, log[-3000:]
+    assert ("batched internal forces on the GPU" in log) == hooked, log[-3000:]
