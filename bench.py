@@ -503,6 +503,15 @@ def run_ours(args):
                                 "cores": cpu.get("threads", 1), "kind": kind,
                                 "sample": f"{cpu['nelem']} LSpace elements (40x20x20 sample of the same beam) assembled by the "
                                           f"reference's EngngModel::assemble into CompCol; 20 IML CG iterations at nnz {cpu['nnz']}"}
+    if world == 1 and not args.no_e2e_executable and not args.no_cpu_baseline:
+        # OOFEM's own executable with the plugin against the unmodified reference executable, same generated input, to
+        # convergence (outside every timed region above; wall-clock of whole processes)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import e2e_executable
+            line["e2e_executable"] = e2e_executable.measure((125, 32, 32), "1e-3")
+        except Exception as ex:          # never let the optional leg take the bench line down
+            line["e2e_executable"] = {"unavailable": repr(ex)}
     if parity is not None:
         line["parity"] = parity
     sys.stdout.flush()
@@ -528,6 +537,8 @@ def main():
     ap.add_argument("--ref-sample-elems", type=int, default=32000, help="reference arm: elements assembled per timed step")
     ap.add_argument("--ref-sample-cg", type=int, default=5, help="reference arm: CG iterations per timed step")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the multi-GPU parity cases after the timed region")
+    ap.add_argument("--no-e2e-executable", action="store_true",
+                    help="N = 1: skip the oofem_cuda -f vs oofem -f comparison on a generated 128k-hex input (about a minute)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu profiling runs only)")
     ap.add_argument("--no-kernel-events", action="store_true", help="scratch: no per-kernel CUDA events in the timed region (no roofline)")

@@ -38,6 +38,7 @@ ConvergedReason CudaCGSolver :: solve(SparseMtrx &A, FloatArray &b, FloatArray &
     if ( !M ) {
         OOFEM_ERROR("cudacg needs a cudacsr matrix (smtype 11), got %s", A.giveClassName());
     }
+    CudaPhaseTimer timer("solve_s");
     int it = 0;
     double res = 0.;
     int flag = ob200_cg_solve(M->giveHandle(), b.givePointer(), x.givePointer(), precondType, maxite, tol, & it, & res, 0);

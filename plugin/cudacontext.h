@@ -13,6 +13,17 @@ public:
     static ob200_context *get();
     /// OOFEM_ERROR with the library's message when rc < 0; returns rc otherwise.
     static int check(int rc, const char *what);
+    /// Wall-clock phase timers of the plugin (printed as one "CudaTiming" line at exit when OOFEM_B200_TIMING is set;
+    /// bench.py's e2e_executable reads it): t is added to the named phase.
+    static void addTime(const char *phase, double seconds);
+    static double now();
+};
+/// adds the life time of the object to a phase
+struct CudaPhaseTimer {
+    const char *phase;
+    double t0;
+    explicit CudaPhaseTimer(const char *p) : phase(p), t0(CudaContext :: now()) { }
+    ~CudaPhaseTimer() { CudaContext :: addTime(phase, CudaContext :: now() - t0); }
 };
 } // namespace oofem
 #endif

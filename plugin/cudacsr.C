@@ -49,6 +49,7 @@ CudaCSR :: ~CudaCSR()
 
 int CudaCSR :: buildInternalStructure(EngngModel *eModel, int di, const UnknownNumberingScheme &s)
 {
+    CudaPhaseTimer timer("structure_s");
     // the pattern CompCol builds (compcol.C:174-267): union over elements of loc x loc, plus the
     // location arrays of the active boundary conditions
     Domain *domain = eModel->giveDomain(di);
@@ -344,6 +345,7 @@ struct BatchedDomain {
 
     bool build(EngngModel *eModel, TimeStep *tStep, const UnknownNumberingScheme &s, Domain *d)
     {
+        CudaPhaseTimer timer("elemset_build_s");
         nelem = d->giveNumberOfElements();
         nnode = d->giveNumberOfDofManagers();
         if ( nelem == 0 || nnode == 0 ) {
@@ -504,6 +506,7 @@ bool CudaCSR :: assembleBatched(EngngModel *eModel, TimeStep *tStep, const Matri
     if ( typeid( ma ) != typeid( TangentAssembler ) ) {
         return false;
     }
+    CudaPhaseTimer timer("assemble_matrix_s");
     BatchedDomain &bd = batchedDomains() [ domain ];
     ob200_elemset *set = bd.get(eModel, tStep, s, domain);
     if ( !set ) {
@@ -536,6 +539,7 @@ bool batchedAssembleVector(EngngModel *eModel, FloatArray &answer, TimeStep *tSt
     if ( it == batchedDomains().end() ) {
         return false;                               // no cudacsr matrix on this domain: not our job
     }
+    CudaPhaseTimer timer("assemble_vector_s");
     BatchedDomain &bd = it->second;
     ob200_elemset *set = bd.get(eModel, tStep, s, domain);
     if ( !set || answer.giveSize() != bd.neq ) {
@@ -563,6 +567,7 @@ void batchedUpdate(EngngModel *eModel, TimeStep *tStep, Domain *domain)
     if ( it == batchedDomains().end() || !it->second.set || CudaCSR :: batchedVectorCalls == 0 ) {
         return;
     }
+    CudaPhaseTimer timer("status_update_s");
     BatchedDomain &bd = it->second;
     // Strains, stresses (and the MisesMat variables) of the converged state into the temporary statuses of the host
     // elements: Element::updateYourself, which runs next, commits them (structuralelement.C:944, misesmat.C:672-690),
