@@ -248,6 +248,27 @@ def oracle_sample(dims, cg_iters):
 # our arm
 # ---------------------------------------------------------------------------------------
 
+def pin_to_gpu_numa_node(device):
+    """Restrict this rank to the host cores NVML lists as local to its GPU, so that the pinned host buffers of the end-to-end
+    leg (first touch) and the copy threads sit on the GPU's NUMA node: with eight ranks on one host the uploads otherwise
+    cross the socket interconnect.  Returns the number of cores, or None when NVML gives no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+        allowed = set(os.sched_getaffinity(0))
+        cores = [c for c in cores if c in allowed]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     from oofem_b200 import capi
@@ -271,6 +292,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -278,6 +300,9 @@ def run_ours(args):
     ctx = capi.Context(local)
     dev = torch.device("cuda", local)
     nx, ny, nz = args.nx, args.ny, args.nz
+    if args.scaling == "strong":
+        # the beam of --nx elements is cut into `world` x-slabs (a remainder of nx / world is dropped: say so in config)
+        nx = max(1, args.nx // world)
     pb = slab_problem(nx, ny, nz, rank, world)
     nelem, neq = pb["conn"].shape[0], pb["neq"]
     matparams = np.array([[capi.MAT_ISOLE, 210e3, 0.3, 0, 0, 0, 0, 0]], dtype=np.float64)
@@ -466,13 +491,15 @@ def run_ours(args):
         "pcg_nnz_iters_per_s": args.cg_iters / (t_cg * 1e-3) * float(nnz) * world,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
         "ms_assembly": t_asm, "ms_pcg": t_cg,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(nx, ny, nz),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(nx, ny, nz) if args.scaling == "weak" else
+                               f"strong scaling: one {nx * world}x{ny}x{nz} = {nx * world * ny * nz} hex LSpace beam cut into {world} x-slabs "
+                               f"of {nx}x{ny}x{nz}, FP64 PCG (BASELINE.json configs[4] pattern at the configs[1] size)",
                    "nelem_per_gpu": nelem, "neq_per_gpu": neq, "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
                    "precond": "diag", "partition": f"{world} x-slabs, shared-plane halo" if world > 1 else "none",
                    "transport": ("peer memory (CUDA IPC mailboxes over NVLink)" if comm.p2p else "NCCL") if comm else "none",
                    "l2": "inputs larger than L2 (val+colind ~3 GB per pass vs 126 MB L2), no flush needed",
-                   "structure_build_s": round(t_structure, 4)},
+                   "structure_build_s": round(t_structure, 4), "host_cores_local_to_gpu": numa},
         "roofline": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                      "frac": spmv_gbs / peak, "traffic": spmv_traffic, "peak_source": peak_src,
                      "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
@@ -534,6 +561,8 @@ def main():
     ap.add_argument("--ny", type=int, default=64)
     ap.add_argument("--nz", type=int, default=64)
     ap.add_argument("--cg-iters", type=int, default=50)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --nx x ny x nz elements per GPU (default, the driver's contract); strong: --nx in total, cut into N slabs")
     ap.add_argument("--ref-sample-elems", type=int, default=32000, help="reference arm: elements assembled per timed step")
     ap.add_argument("--ref-sample-cg", type=int, default=5, help="reference arm: CG iterations per timed step")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the multi-GPU parity cases after the timed region")

@@ -413,6 +413,197 @@ cg_scalars_p2p_kernel(int stage, int iter, double tol, double *__restrict__ red,
     }
 }
 
+
+// ---- distributed iteration tail in ONE cooperative launch ------------------------------------------------------------
+// Everything of a distributed CG iteration behind the product (which has pushed this rank's sums of the shared rows into
+// the sharers' mailboxes in its epilogue): halo pull, all-gather of p.q, x/r update, all-gather of r.r and r.z, p update
+// for the next iteration.  Five launches of the round-1 sequence (halo_pull_kernel, cg_scalars_p2p_kernel,
+// cg_update_xr_kernel, cg_scalars_p2p_kernel, cg_update_p_kernel) become one; product + tail = two launches per iteration,
+// as on one GPU.  The grid barriers are cooperative-groups grid syncs; the two scalar exchanges are done by warp 0 of
+// CTA 0 through the mailboxes exactly as in cg_scalars_p2p_kernel (same words, same rank order on every rank; the
+// per-CTA partial sums are grouped differently from the six-launch path, so the two paths agree to round-off only).
+struct CgTailArgs {
+    int32_t neq;
+    double *x, *r, *p, *q;
+    const double *diag;
+    const unsigned char *owned;
+    const double *spmv_partials;
+    int nA;
+    double *partials;                       // [3][P]: pull p.q | r.r | r.z per CTA
+    int P;
+    double *red;
+    int iter;
+    double tol;
+    CgScalars *S;
+    // halo pull (halo_pull_kernel)
+    const int32_t *ueq, *uptr, *umb, *ubefore;
+    const unsigned long long *mail;
+    unsigned int seq_halo;
+    int64_t nuniq;
+    // scalar all-gathers (cg_scalars_p2p_kernel)
+    int nranks;
+    unsigned long long *const *peer_sdata;
+    const unsigned long long *own_sdata;
+    int64_t half1, half2;
+    unsigned int seq1, seq2;
+    int *error;
+};
+
+// wait for the two words of a mailbox entry (comm_p2p.cu: ll_load); false on timeout
+__device__ __forceinline__ bool cg_ll_load(const unsigned long long *slot, unsigned int seq, double &v)
+{
+    unsigned long long w0, w1, t0 = 0, t1;
+    for ( int spin = 0;; spin++ ) {
+        asm volatile( "ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"( w0 ), "=l"( w1 ) : "l"( slot ) : "memory" );
+        if ( (unsigned int)( w0 >> 32 ) == seq && (unsigned int)( w1 >> 32 ) == seq ) break;
+        if ( spin == 64 ) asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t0 ) );
+        if ( spin > 64 ) {
+            asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t1 ) );
+            if ( t1 - t0 > 4000000000ull ) return false;
+            __nanosleep(32);
+        }
+    }
+    v = __longlong_as_double((long long)( ( w0 & 0xffffffffull ) | ( w1 << 32 ) ));
+    return true;
+}
+
+// warp 0 of one CTA: all-gather red[0..nred) over the ranks (lane r talks to rank r), sum in rank order, scalar update
+__device__ __forceinline__ void cg_scalars_allgather(int stage, int iter, double tol, double *red, int nred, CgScalars *S, int nranks,
+                                                     unsigned long long *const *peer_sdata, const unsigned long long *own_sdata,
+                                                     int64_t half_words, unsigned int seq, int *error)
+{
+    const int lane = threadIdx.x;
+    if ( lane < nranks )
+        for ( int j = 0; j < nred; j++ ) ll_store(peer_sdata[lane] + half_words + 2 * j, red[j], seq);
+    double v[kRedMax] = { 0.0, 0.0, 0.0 };
+    bool ok = true;
+    if ( lane < nranks )
+        for ( int j = 0; j < nred && ok; j++ ) ok = cg_ll_load(own_sdata + half_words + 2 * ( (int64_t) lane * 4 + j ), seq, v[j]);
+    if ( !__all_sync(0xffffffffu, ok) ) {
+        if ( lane == 0 ) { atomicExch(error, 1); S->done = 1; }
+        return;
+    }
+    double tot[kRedMax] = { 0.0, 0.0, 0.0 };
+    for ( int r = 0; r < nranks; r++ )
+#pragma unroll
+        for ( int j = 0; j < kRedMax; j++ ) tot[j] += __shfl_sync(0xffffffffu, v[j], r);
+    if ( lane == 0 ) {
+        for ( int j = 0; j < nred; j++ ) red[j] = tot[j];
+        cg_scalars(stage, iter, tol, tot, S);
+    }
+}
+
+__global__ void __launch_bounds__(kCgThreads)
+cg_tail_p2p_kernel(CgTailArgs a)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double scratch[32];
+    volatile CgScalars *Sv = a.S;
+    if ( Sv->done ) return;                  // uniform: S is only written behind grid barriers
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x, first = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    // ---- halo pull: q[shared row] = sum over the sharers in rank order; p.q over the shared rows this rank owns ----
+    {
+        double dot = 0.0;
+        bool ok = true;
+        for ( int64_t u = first; u < a.nuniq; u += stride ) {
+            const int b = a.uptr[u], e = a.uptr[u + 1], nb = a.ubefore[u];
+            const int row = a.ueq[u];
+            const double own = a.q[row];
+            double acc = 0.0;
+            for ( int t = b; t < e; t++ ) {
+                if ( t - b == nb ) acc += own;
+                double v = 0.0;
+                ok = cg_ll_load(a.mail + 2 * (int64_t) a.umb[t], a.seq_halo, v) && ok;
+                acc += v;
+            }
+            if ( nb == e - b ) acc += own;
+            a.q[row] = acc;
+            if ( a.owned[row] ) dot += a.p[row] * acc;
+        }
+        if ( !ok ) atomicExch(a.error, 1);
+        dot = block_sum(dot, scratch);
+        if ( threadIdx.x == 0 ) a.partials[blockIdx.x] = dot;
+    }
+    __threadfence();
+    grid.sync();
+    // ---- alpha = rho / p.q over all ranks ----
+    if ( blockIdx.x == 0 ) {
+        const double s0 = sum_partials(a.spmv_partials, a.nA, scratch);
+        __syncthreads();
+        const double s1 = sum_partials(a.partials, gridDim.x, scratch);
+        if ( threadIdx.x == 0 ) a.red[0] = s0 + s1;
+        __syncthreads();
+        if ( threadIdx.x < 32 )
+            cg_scalars_allgather(1, a.iter, a.tol, a.red, 1, a.S, a.nranks, a.peer_sdata, a.own_sdata, a.half1, a.seq1, a.error);
+    }
+    __threadfence();
+    grid.sync();
+    if ( Sv->done ) return;                  // a peer wait timed out
+    const double alpha = Sv->alpha;
+    // ---- x += alpha p, r -= alpha q, partial sums of r.r and r.z over the owned rows ----
+    {
+        double rr = 0.0, rz = 0.0;
+        int64_t i = first;
+        // three independent elements per trip: eighteen loads in flight per thread
+        for ( ; i + 2 * stride < a.neq; i += 3 * stride ) {
+            const int64_t j = i + stride, k = j + stride;
+            const double pi = a.p[i], pj = a.p[j], pk = a.p[k], qi = a.q[i], qj = a.q[j], qk = a.q[k];
+            const double xi = a.x[i], xj = a.x[j], xk = a.x[k], r0i = a.r[i], r0j = a.r[j], r0k = a.r[k];
+            const double di = a.diag ? a.diag[i] : 1.0, dj = a.diag ? a.diag[j] : 1.0, dk = a.diag ? a.diag[k] : 1.0;
+            const double oi = a.owned[i] ? 1.0 : 0.0, oj = a.owned[j] ? 1.0 : 0.0, ok = a.owned[k] ? 1.0 : 0.0;
+            const double ri = r0i - alpha * qi, rj = r0j - alpha * qj, rk = r0k - alpha * qk;
+            a.x[i] = xi + alpha * pi; a.x[j] = xj + alpha * pj; a.x[k] = xk + alpha * pk;
+            a.r[i] = ri; a.r[j] = rj; a.r[k] = rk;
+            if ( oi != 0.0 ) { rr += ri * ri; rz += ri * ( a.diag ? ri * di : ri ); }
+            if ( oj != 0.0 ) { rr += rj * rj; rz += rj * ( a.diag ? rj * dj : rj ); }
+            if ( ok != 0.0 ) { rr += rk * rk; rz += rk * ( a.diag ? rk * dk : rk ); }
+        }
+        for ( ; i < a.neq; i += stride ) {
+            a.x[i] += alpha * a.p[i];
+            const double ri = a.r[i] - alpha * a.q[i];
+            a.r[i] = ri;
+            if ( a.owned[i] ) {
+                rr += ri * ri;
+                rz += ri * ( a.diag ? ri * a.diag[i] : ri );
+            }
+        }
+        rr = block_sum(rr, scratch);
+        if ( threadIdx.x == 0 ) a.partials[a.P + blockIdx.x] = rr;
+        rz = block_sum(rz, scratch);
+        if ( threadIdx.x == 0 ) a.partials[2 * a.P + blockIdx.x] = rz;
+    }
+    __threadfence();
+    grid.sync();
+    // ---- residual test, rho, beta over all ranks ----
+    if ( blockIdx.x == 0 ) {
+        const double s0 = sum_partials(a.partials + a.P, gridDim.x, scratch);
+        __syncthreads();
+        const double s1 = sum_partials(a.partials + 2 * a.P, gridDim.x, scratch);
+        if ( threadIdx.x == 0 ) { a.red[0] = s0; a.red[1] = s1; }
+        __syncthreads();
+        if ( threadIdx.x < 32 )
+            cg_scalars_allgather(2, a.iter, a.tol, a.red, 2, a.S, a.nranks, a.peer_sdata, a.own_sdata, a.half2, a.seq2, a.error);
+    }
+    __threadfence();
+    grid.sync();
+    if ( Sv->done ) return;                  // converged (cg.h:60-64), or a peer wait timed out
+    const double beta = Sv->beta;
+    // ---- p = z + beta p for the next iteration (cg.h:45-52) ----
+    int64_t i = first;
+    for ( ; i + 2 * stride < a.neq; i += 3 * stride ) {
+        const int64_t j = i + stride, k = j + stride;
+        const double ri = a.r[i], rj = a.r[j], rk = a.r[k], pi = a.p[i], pj = a.p[j], pk = a.p[k];
+        const double di = a.diag ? a.diag[i] : 1.0, dj = a.diag ? a.diag[j] : 1.0, dk = a.diag ? a.diag[k] : 1.0;
+        a.p[i] = ( a.diag ? ri * di : ri ) + beta * pi;
+        a.p[j] = ( a.diag ? rj * dj : rj ) + beta * pj;
+        a.p[k] = ( a.diag ? rk * dk : rk ) + beta * pk;
+    }
+    for ( ; i < a.neq; i += stride ) {
+        const double z = a.diag ? a.r[i] * a.diag[i] : a.r[i];
+        a.p[i] = z + beta * a.p[i];
+    }
+}
+
 struct CgWork {
     double *r, *p, *q, *partials, *red;
     CgScalars *S;
@@ -425,16 +616,16 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
     const int32_t n = A->neq;
     const int P = kCgMaxBlocks;                         // stride between the partial arrays
     const int G = ctx->shape.grid(n, kCgThreads, 8);    // CTAs of the vector kernels (<= 148*8 <= P)
-    const int64_t need = 3 * (int64_t) n + (int64_t) kRedMax * P + kRedMax + 16;
+    const int64_t need = 3 * (int64_t) n + (int64_t)( kRedMax + 1 ) * P + kRedMax + 16;
     if ( A->work.n < need ) OB_CHECK( A->work.alloc(need) );
     CgWork w;
     w.r = A->work.p;
     w.p = w.r + n;
     w.q = w.p + n;
     w.partials = w.q + n;
-    w.red = w.partials + (int64_t) kRedMax * P;
+    w.red = w.partials + (int64_t)( kRedMax + 1 ) * P;         // [kRedMax][P] reduction partials + [P] the product's p.q partials (distributed tail)
     w.S = reinterpret_cast< CgScalars * >( w.red + kRedMax + 1 );
-    OB_CUDA( cudaMemsetAsync(w.partials, 0, sizeof( double ) * ( (size_t) kRedMax * P + kRedMax + 16 ), ctx->stream) );
+    OB_CUDA( cudaMemsetAsync(w.partials, 0, sizeof( double ) * ( (size_t)( kRedMax + 1 ) * P + kRedMax + 16 ), ctx->stream) );
     const unsigned char *owned = comm ? comm->owned.p : nullptr;
     const bool dist = comm && comm->nranks > 1;
 
@@ -510,15 +701,62 @@ static int cg_run(ob200_csr *A, ob200_comm *comm, const double *b_dev, double *x
         cudaGetLastError();
     }
 
+    // distributed over peer memory: the same idea, with the halo pull and the two scalar exchanges inside the launch
+    bool dcoop = false;
+    if ( fused_halo && n > 0 && !( getenv("OB200_CG_COOP") && getenv("OB200_CG_COOP")[0] == '0' ) ) {
+        int can = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, ctx->device);
+        if ( can && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_tail_p2p_kernel, kCgThreads, 0) == cudaSuccess && per_sm > 0 ) {
+            coop_grid = per_sm * ctx->shape.sms;
+            if ( coop_grid > G ) coop_grid = G;
+            dcoop = coop_grid <= kCgMaxBlocks && coop_grid <= P;
+        }
+        cudaGetLastError();
+    }
+
     CgScalars h;
-    const int poll = 8;
+    const int poll = ( coop || dcoop ) ? 32 : 8;       // iterations enqueued between two looks at the device-side stop flag
     int it = 0;
     bool done = false;
     while ( !done ) {
         int batch_end = it + poll < max_iter ? it + poll : max_iter;
         for ( ; it < batch_end; ) {
             it++;
-            if ( !coop || it == 1 ) OB_LAUNCH(ctx, cg_update_p_kernel, G, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
+            if ( !( coop || dcoop ) || it == 1 ) OB_LAUNCH(ctx, cg_update_p_kernel, G, kCgThreads, 0, n, w.r, diag, w.p, it == 1 ? 1 : 0, w.S);
+            if ( dcoop ) {
+                // two launches per iteration: the product (p.q partials of the unshared rows, shared rows pushed to the
+                // sharers), then the cooperative tail
+                const unsigned int seq = ++comm->halo_seq;
+                const SpmvHalo hv{ comm->route.p, comm->uniq_ptr.p, comm->push_dst.p, 2 * (int64_t)( seq & 1u ) * ML.data_half, seq };
+                int nb = 0;
+                OB_CHECK( spmv_fused_halo(A, w.p, w.q, w.partials + 3 * (int64_t) P, &nb, &w.S->done, hv) );
+                CgTailArgs ta;
+                ta.neq = n; ta.x = x_dev; ta.r = w.r; ta.p = w.p; ta.q = w.q; ta.diag = diag; ta.owned = owned;
+                ta.spmv_partials = w.partials + 3 * (int64_t) P; ta.nA = nb; ta.partials = w.partials; ta.P = P; ta.red = w.red;
+                ta.iter = it; ta.tol = tol; ta.S = w.S;
+                ta.ueq = comm->uniq_eq.p; ta.uptr = comm->uniq_ptr.p; ta.umb = comm->uniq_mb.p; ta.ubefore = comm->uniq_before.p;
+                ta.mail = reinterpret_cast< const unsigned long long * >( comm->mailbox + ML.data ) + 2 * (int64_t)( seq & 1u ) * ML.data_half;
+                ta.seq_halo = seq; ta.nuniq = comm->nuniq;
+                ta.nranks = comm->nranks; ta.peer_sdata = comm->p_sdata.p;
+                ta.own_sdata = reinterpret_cast< const unsigned long long * >( comm->mailbox + ML.sdata );
+                ta.seq1 = ++comm->scal_seq; ta.half1 = 2 * (int64_t)( ta.seq1 & 1u ) * ML.sdata_half;
+                ta.seq2 = ++comm->scal_seq; ta.half2 = 2 * (int64_t)( ta.seq2 & 1u ) * ML.sdata_half;
+                ta.error = reinterpret_cast< int * >( comm->mailbox + ML.error );
+                void *args[] = { &ta };
+                ob200_prof_rec pr = { "cg_tail_p2p_kernel", nullptr, nullptr };
+                if ( ctx->profiling ) {
+                    pr.start = ctx->prof_event();
+                    pr.stop = ctx->prof_event();
+                    cudaEventRecord(pr.start, ctx->stream);
+                }
+                OB_CUDA( cudaLaunchCooperativeKernel((void *) cg_tail_p2p_kernel, dim3(coop_grid), dim3(kCgThreads), args, 0, ctx->stream) );
+                if ( ctx->profiling ) {
+                    cudaEventRecord(pr.stop, ctx->stream);
+                    ctx->prof_pending.push_back(pr);
+                }
+                ctx->launches++;
+                continue;
+            }
             if ( coop ) {
                 // two launches per iteration: the product with its p.q partials, then everything else
                 int nb = 0;

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+@pytest.mark.parametrize("transport", ["p2p", "nccl", "p2p_sixlaunch"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_distributed_assembly_halo_and_pcg_vs_oracle(world, transport):
     import torch
@@ -23,11 +23,12 @@ def test_distributed_assembly_halo_and_pcg_vs_oracle(world, transport):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tests", "dist_worker.py")], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, OB200_P2P="1" if transport == "p2p" else "0"))
+                       env=dict(os.environ, OB200_P2P="0" if transport == "nccl" else "1",
+                                OB200_CG_COOP="0" if transport == "p2p_sixlaunch" else "1"))
     import re
     lines = [json.loads(m) for m in re.findall(r"\{[^{}]*\}", r.stdout)]      # ranks may share a line
     # four cases (LSpace / LTRSpace x slab / box), one line each from rank 0
     assert r.returncode == 0 and len(lines) == 4 and all(l["ok"] for l in lines), (r.stdout[-3000:], r.stderr[-3000:])
-    assert all(l["transport_used"] == transport for l in lines), lines
+    assert all(l["transport_used"] == transport.split("_")[0] for l in lines), lines
     if world >= 4:
         assert max(l["max_sharers"] for l in lines) >= 4, lines
