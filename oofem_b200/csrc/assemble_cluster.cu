@@ -682,6 +682,9 @@ __device__ __forceinline__ void cl_fail(int code)
 {
     if ( cl_error_word ) atomicExch(cl_error_word, code);
 }
+#ifndef OB200_CL_RELAX_NS
+#define OB200_CL_RELAX_NS 200
+#endif
 #ifndef OB200_CL_WAIT_HINT_NS
 #define OB200_CL_WAIT_HINT_NS 20000
 #endif
@@ -689,26 +692,50 @@ __device__ __forceinline__ void cl_fail(int code)
 #define OB200_CL_BOUNDED 1
 #endif
 constexpr unsigned int kClSpinLimit = OB200_CL_BOUNDED ? 1u << 20 : 0xFFFFFFFFu;      // try_wait rounds (each suspends for a hardware-defined time) / polls
+// slow path of cl_mbar_wait: bounded polling (kept out of line: the contraction warps' code stays as small as with a bare loop)
+__device__ __noinline__ void cl_mbar_wait_slow(uint32_t bar, uint32_t parity, volatile unsigned int *failed)
+{
+    for ( unsigned int n = 0; n < kClSpinLimit; n++ ) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"( ok ) : "r"( bar ), "r"( parity ) : "memory" );
+        if ( ok ) return;
+    }
+    *failed = 1u;
+}
+// the contraction warps' wait: almost always the phase is complete already (the other roles run ahead)
 __device__ __forceinline__ void cl_mbar_wait(unsigned long long *bar, uint32_t parity, volatile unsigned int *failed)
 {
-    // try_wait suspends the thread until the phase completes or the time hint (ns) runs out: the loop body runs rarely, so the
-    // round counter that bounds the wait costs nothing while other warps work
     uint32_t ok;
     asm volatile(
         "{\n"
-        ".reg .pred p, q;\n"
-        ".reg .u32 n;\n"
-        "mov.u32 n, 0;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n"
-        "@p bra DONE_%=;\n"
-        "add.u32 n, n, 1;\n"
-        "setp.lt.u32 q, n, %3;\n"
-        "@q bra WAIT_%=;\n"
-        "DONE_%=:\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"( ok ) : "r"( cl_smem(bar) ), "r"( parity ), "r"( kClSpinLimit ), "r"( (uint32_t) OB200_CL_WAIT_HINT_NS ) : "memory" );
-    if ( !ok ) *failed = 1u;      // shared-memory word, reported when the role's loop ends (cl_fail)
+        "}\n" : "=r"( ok ) : "r"( cl_smem(bar) ), "r"( parity ) : "memory" );
+    if ( !ok ) cl_mbar_wait_slow(cl_smem(bar), parity, failed);
+}
+// The wait of the warps that run ahead of the contraction warps (producer thread, geometry warps): try_wait returns quickly when
+// the phase is not complete, so a bare loop spins at full issue rate on a scheduler it shares with two contraction warps (the
+// five-instruction bounded loop above cost 12 % of the kernel when every role used it).  Here the poll is followed by a sleep.
+__device__ __forceinline__ void cl_mbar_wait_relaxed(unsigned long long *bar, uint32_t parity, volatile unsigned int *failed)
+{
+    for ( unsigned int n = 0; n < kClSpinLimit; n++ ) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"( ok ) : "r"( cl_smem(bar) ), "r"( parity ) : "memory" );
+        if ( ok ) return;
+        __nanosleep(OB200_CL_RELAX_NS);
+    }
+    *failed = 1u;
 }
 __device__ __forceinline__ void cl_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
@@ -860,14 +887,14 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
             const ClBlob *blob = V.blobs + w.st;
             const int rec_begin = blob->hdr.rec_begin, npk = blob->hdr.npk, nblocks = blob->hdr.nblocks;
             const int b = bseq & 1;
-            if ( bseq >= 2 ) cl_mbar_wait(&sh.blob_empty[b], ( ( bseq >> 1 ) - 1 ) & 1, &sh.failed);
+            if ( bseq >= 2 ) cl_mbar_wait_relaxed(&sh.blob_empty[b], ( ( bseq >> 1 ) - 1 ) & 1, &sh.failed);
             const uint32_t bytes = (uint32_t)( kBlobHead + ( ( nblocks * 4 + 15 ) & ~15 ) );
             cl_mbar_expect_tx(&sh.blob_full[b], bytes);
             cl_bulk_load(&sh.blob[b], blob, bytes, &sh.blob_full[b]);
             for ( int k = 0; k < npk; k += kChunkPk, cseq++ ) {
                 const int s = cseq % kChunks, n = min(kChunkPk, npk - k);
                 const unsigned int round = cseq / kChunks;
-                if ( round > 0 ) cl_mbar_wait(&sh.empty_r[s], ( round - 1 ) & 1, &sh.failed);
+                if ( round > 0 ) cl_mbar_wait_relaxed(&sh.empty_r[s], ( round - 1 ) & 1, &sh.failed);
                 if ( n < kChunkPk ) cl_mbar_arrive_n(&sh.empty_r[s], ( kChunkPk - n ) * 4);      // the records a short chunk lacks
                 cl_mbar_expect_tx(&sh.full_p[s], n * kPacketBytes);
                 cl_bulk_load(sh.rec[s], V.recs + rec_begin + 4 * k, n * kPacketBytes, &sh.full_p[s]);
@@ -887,8 +914,8 @@ lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
                 if ( (int)( pseq % kGWarps ) != g ) continue;
                 const unsigned int cseq = cseq0 + k / kChunkPk;
                 const int cs = cseq % kChunks, hs = pseq % kHSlots;
-                cl_mbar_wait(&sh.full_p[cs], ( cseq / kChunks ) & 1, &sh.failed);
-                if ( pseq >= kHSlots ) cl_mbar_wait(&sh.empty_h[hs], ( pseq / kHSlots - 1 ) & 1, &sh.failed);
+                cl_mbar_wait_relaxed(&sh.full_p[cs], ( cseq / kChunks ) & 1, &sh.failed);
+                if ( pseq >= kHSlots ) cl_mbar_wait_relaxed(&sh.empty_h[hs], ( pseq / kHSlots - 1 ) & 1, &sh.failed);
                 const ClRecord &R = sh.rec[cs][( k % kChunkPk ) * 4 + ( lane >> 3 )];
                 if ( R.elem >= 0 && !( kAblate & 8 ) ) cl_geometry(R.xyz, lane & 7, R.slotof, sh.H[hs][lane >> 3]);
                 __syncwarp();
