@@ -1,22 +1,24 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, smoke, bench, ncu launch list, ncu full capture of the top kernels.
+# One GPU-box pass: parity tests, smoke, bench (both arms), ncu launch list, ncu full capture of the top kernels.
 # Usage (under gpurun): bash scripts/gpu_check.sh [tag]
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
-echo "== pytest -m gpu" 
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log
+echo "== pytest -m gpu"
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_$TAG.log
 echo "== smoke"
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke_$TAG.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log
 echo "== bench"
-timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
-echo "== bench reference arm"
-timeout 900 python bench.py --impl reference --steps 2 --warmup 0 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
+timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; head -c 600 $OUT/bench_$TAG.json; echo; tail -3 $OUT/bench_$TAG.err
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --cg-iters 20 --no-cpu-baseline --no-e2e > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 echo "== ncu full"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'spmv_block_kernel|spmv_stream_kernel|lspace_gather_kernel|lspace_stiffness_kernel|cg_update_xr_kernel' -c 9 \
-    -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --cg-iters 4 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
-ls -la $OUT
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'spmv_block_kernel|lspace_cluster_kernel|cg_xr_p_kernel' -c 6 \
+    -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --cg-iters 2 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+if [ "$2" = "ref" ]; then
+echo "== bench reference arm"
+timeout 1700 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json | head -c 1500; echo
+fi
+ls -la $OUT | tail -12

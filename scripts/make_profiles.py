@@ -65,20 +65,25 @@ if os.path.exists(rep):
                     f.write(f"    {k:82s} {r[i]} {units[i]}\n")
     # DRAM bytes per launch of the two dominant kernels -> profiles/traffic.json (bench.py roofline.traffic)
     import json
-    traffic = {"source": f"ncu --set full ({tag}), dram__bytes_read.sum + dram__bytes_write.sum per launch at the 1M-hex config"}
+    tj = os.path.join(P, "traffic.json")
+    traffic = json.load(open(tj)) if os.path.exists(tj) else {}      # kernels absent from this capture keep their entry
+    src = traffic.get("sources", {})
     conv = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     ir, iw, ik = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('Kernel Name')
     best = {}
     for r in rows[2:]:
-        for key in ("spmv_block_kernel", "spmv_stream_kernel", "lspace_gather_kernel"):
+        for key in ("spmv_block_kernel", "spmv_stream_kernel", "lspace_gather_kernel", "lspace_cluster_kernel"):
             if key in r[ik]:
                 b = float(r[ir].replace(',', '')) * conv.get(units[ir], 1.0) + float(r[iw].replace(',', '')) * conv.get(units[iw], 1.0)
                 best.setdefault(key, []).append(b)
     for key, v in best.items():
         v.sort()
         traffic[key] = v[len(v) // 2]          # median launch
-    if len(traffic) > 1:
-        json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+        src[key] = tag
+    traffic["source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at the 1M-hex config (capture per kernel: sources)"
+    traffic["sources"] = src
+    if best:
+        json.dump(traffic, open(tj, "w"), indent=1)
 for fn in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
     if os.path.exists(os.path.join(G, fn)):
         shutil.copy(os.path.join(G, fn), os.path.join(P, fn))
