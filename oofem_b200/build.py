@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liboofem_b200.so")
-SOURCES = ["context.cu", "csr.cu", "element_kernels.cu", "assemble_gather.cu", "assemble_cluster.cu", "cg.cu", "comm.cu", "comm_p2p.cu"]
+SOURCES = ["context.cu", "csr.cu", "element_kernels.cu", "assemble_gather.cu", "assemble_cluster.cu", "assemble_tet.cu", "assemble_strips.cu", "cg.cu", "comm.cu", "comm_p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

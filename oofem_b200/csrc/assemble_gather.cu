@@ -951,7 +951,7 @@ lspace_gather_kernel(ElemSetView S, GatherView G, int32_t ngroups, const int32_t
 int gather_prepare_mesh(ob200_elemset *S)
 {
     ob200_context *ctx = S->ctx;
-    if ( S->etype != OB200_LSPACE || S->nelem == 0 || S->nnode == 0 ) return OB200_OK;
+    if ( S->nelem == 0 || S->nnode == 0 ) return OB200_OK;
     const int64_t n = S->nelem * S->nen;
     OB_REQUIRE(n < (int64_t) INT_MAX / 8, OB200_ECAPACITY, "elemset: %lld element nodes exceed the 32-bit visit index", (long long) n);
     S->nvisit = n;
@@ -976,10 +976,15 @@ int gather_prepare_mesh(ob200_elemset *S)
     OB_CHECK( S->ninc_start.alloc(S->nnode + 1) );
     OB_CHECK( narrow_i64_to_i32(ctx, start64.p, S->ninc_start.p, S->nnode + 1) );
     OB_CHECK( S->ninc.alloc(n) );
-    OB_CHECK( S->ninc_node.alloc(n) );
     OB_LAUNCH(ctx, node_incidence_fill_kernel, grid, 256, 0, S->conn.p, n, S->nen, S->ninc_start.p, fill.p, S->ninc.p);
     OB_LAUNCH(ctx, node_incidence_sort_kernel, ctx->shape.grid(S->nnode, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p);
     OB_CHECK( max_reduce(ctx, cnt.p, S->nnode, &S->maxval) );
+    OB_CHECK( S->nodeeq.alloc(S->nnode * 3) );
+    OB_CUDA( cudaMemsetAsync(S->nodeeq.p, 0, sizeof( int32_t ) * (size_t) S->nnode * 3, ctx->stream) );
+    OB_CHECK( elemset_await_loc(S) );
+    OB_LAUNCH(ctx, node_equations_kernel, grid, 256, 0, S->conn.p, S->loc.p, S->nelem, S->nen, S->nodeeq.p);
+    if ( S->etype != OB200_LSPACE ) return OB200_OK;          // the rest is the visit-group schedule of the LSpace kernels
+    OB_CHECK( S->ninc_node.alloc(n) );
     S->ngroups = (int32_t)( ( S->nvisit - 1 ) / kGroupVisits + 1 );
     OB_CHECK( S->gtab.alloc(S->ngroups + 1) );
     OB_LAUNCH(ctx, group_table_kernel, ctx->shape.grid(S->nnode + 1, 256, 8), 256, 0, (int32_t) S->nnode, S->ninc_start.p, S->ngroups, S->gtab.p);
@@ -989,10 +994,6 @@ int gather_prepare_mesh(ob200_elemset *S)
         OB_LAUNCH(ctx, visit_unique_kernel, ctx->shape.grid((int64_t) S->ngroups * 32, 256, 8), 256, 0, S->ngroups, S->gtab.p, S->ninc.p, S->vu.p);
     OB_CHECK( S->exyz.alloc(n * 3) );
     OB_LAUNCH(ctx, element_coords_kernel, grid, 256, 0, S->conn.p, S->coords.p, n, S->exyz.p);
-    OB_CHECK( S->nodeeq.alloc(S->nnode * 3) );
-    OB_CUDA( cudaMemsetAsync(S->nodeeq.p, 0, sizeof( int32_t ) * (size_t) S->nnode * 3, ctx->stream) );
-    OB_CHECK( elemset_await_loc(S) );
-    OB_LAUNCH(ctx, node_equations_kernel, grid, 256, 0, S->conn.p, S->loc.p, S->nelem, S->nen, S->nodeeq.p);
     return OB200_OK;
 }
 
@@ -1001,12 +1002,16 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     ob200_context *ctx = S->ctx;
     S->gather_ok = false;
     S->cluster_ok = false;
-    if ( getenv("OB200_ASSEMBLY") && !strcmp(getenv("OB200_ASSEMBLY"), "slotmap") ) return OB200_OK;      // generic path (cross-checks)
-    if ( S->etype != OB200_LSPACE || S->nelem == 0 || !S->all_isole || !S->ninc.p ) return OB200_OK;
+    S->strips_ok = false;
+    const char *mode = getenv("OB200_ASSEMBLY");
+    if ( mode && !strcmp(mode, "slotmap") ) return OB200_OK;      // generic path (cross-checks)
+    if ( S->etype != OB200_LSPACE || S->nelem == 0 || !S->ninc.p ) return OB200_OK;
+    // sets with a MisesMat (or OB200_ASSEMBLY=strips) take the element-strip assembly, which shares the node-block schedule
+    const bool strips = !S->all_isole || ( mode && !strcmp(mode, "strips") );
     if ( S->maxval > kMaxValence || A->maxrow > kMaxRowLen || A->neq == 0 ) return OB200_OK;
     S->maxblk = ( ( A->maxrow + 3 ) & ~3 );          // a column block is at least one column wide
     if ( S->maxblk < 4 ) S->maxblk = 4;
-    OB_CHECK( S->pos.alloc(S->nvisit * 8) );
+    if ( !strips ) OB_CHECK( S->pos.alloc(S->nvisit * 8) );
     OB_CHECK( S->nblk.alloc(S->nnode) );
     OB_CHECK( S->blk.alloc(S->nnode * S->maxblk) );
     DevBuf< int > flags;
@@ -1014,14 +1019,14 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     OB_CUDA( cudaMemsetAsync(flags.p, 0, sizeof( int ) * 4, ctx->stream) );
     OB_CUDA( cudaMemsetAsync(S->blk.p, 0, sizeof( unsigned short ) * (size_t) S->nnode * S->maxblk, ctx->stream) );
     OB_CHECK( S->ebidx.alloc(S->nvisit * 8) );
-    const bool allpairs = getenv("OB200_NODE_BLOCKS") && !strcmp(getenv("OB200_NODE_BLOCKS"), "allpairs");
+    const bool allpairs = !strips && getenv("OB200_NODE_BLOCKS") && !strcmp(getenv("OB200_NODE_BLOCKS"), "allpairs");
     if ( allpairs ) {
         OB_LAUNCH(ctx, node_blocks_allpairs_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
                   S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
                   reinterpret_cast< unsigned long long * >( flags.p + 2 ));
     } else {
         OB_LAUNCH(ctx, node_blocks_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
-                  S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, S->pos.p, S->nblk.p, S->blk.p, flags.p,
+                  S->conn.p, S->nodeeq.p, A->rowptr.p, A->colind.p, S->maxblk, strips ? nullptr : S->pos.p, S->nblk.p, S->blk.p, flags.p,
                   reinterpret_cast< unsigned long long * >( flags.p + 2 ), S->ebidx.p);
     }
     int h[4] = { 0, 0, 0, 0 };
@@ -1029,7 +1034,8 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );
     // h[0]: the matrix pattern is not the pattern of this element set (or equations of a node are not
     // consecutive); h[1]: capacity -- both keep the generic slot-map path
-    S->gather_ok = ( h[0] == 0 && h[1] == 0 );
+    S->gather_ok = ( h[0] == 0 && h[1] == 0 && !strips );
+    S->strips_ok = ( h[0] == 0 && h[1] == 0 && strips );
     unsigned long long cov;
     memcpy(&cov, h + 2, sizeof( cov ));
     S->covers_all = ( (int64_t) cov == A->nnz );

@@ -1,0 +1,307 @@
+// Owner-computes assembly of the LTRSpace tangent into the cudacsr matrix ("node rows").
+//
+// Replaces EngngModel::assemble (src/core/engngm.C:889-929) + CompCol::assemble (src/core/compcol.C:263-299) for a whole
+// LTRSpace element set (IsotropicLinearElasticMaterial and / or MisesMat) without atomics: the up to three matrix rows of a
+// node are produced by one warp and written once, and the contributions of the elements around the node are added in
+// ascending element number -- bit-reproducible run to run.
+//
+//   * per element (once per mesh): the constant gradients of FEI3dTetLin::evaldNdx (src/core/fei3dtetlin.C:116-166), the
+//     volume (1-point rule, weight 1/6: gaussintegrationrule.C:500-507) and the volume-weighted Lame constants
+//     (isolinearelasticmaterial.C:80-84): 16 doubles.  With a MisesMat in the set also, per call, the 6x6 algorithmic tangent
+//     of the element's Gauss point (MisesMat::give3dMaterialStiffnessMatrix, misesmat.C:493-545).
+//   * per node A: the column blocks (neighbour nodes B) are read off the first free row of A in the CSR structure; one lane
+//     per block walks the elements around A (node -> element incidence built at create), and where the element contains B
+//     adds V B_a^T D B_b (Structural3DElement::computeBmatrixAt, structural3delement.C:63-86) to its 3x3 accumulator.
+//
+// tet_bind verifies what the kernel relies on (the rows of a node have one column pattern, the free equations of a node are
+// consecutive, every block an element produces is in the pattern); otherwise the slot-map path stays in use.
+#include "element_device.cuh"
+#include "elemset.h"
+#include <string.h>
+#include <stdlib.h>
+
+namespace ob200 {
+
+constexpr int kTetWarps = 8;
+constexpr int kTetMaxBlk = 128;          // column blocks of one node's rows
+constexpr int kTetRec = 16;              // doubles per element: g[4][3], V lambda, V mu, V, pad
+
+// eqnode[eq-1] = node*4 + component
+__global__ void tet_eqnode_kernel(int64_t nnode, const int32_t *__restrict__ nodeeq, int32_t *__restrict__ eqnode)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < nnode * 3; t += stride ) {
+        const int eq = nodeeq[t];
+        if ( eq > 0 ) eqnode[eq - 1] = (int32_t)( ( t / 3 ) * 4 + t % 3 );
+    }
+}
+
+// One warp per node.  flags[0]: the structure is not what the kernel assumes; flags[1]: more than kTetMaxBlk column blocks;
+// covered: number of matrix entries the kernel writes.
+__global__ void __launch_bounds__(256)
+tet_rows_check_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const int32_t *__restrict__ ninc,
+                      const int32_t *__restrict__ conn, const int32_t *__restrict__ nodeeq, const int32_t *__restrict__ eqnode,
+                      const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int32_t neq,
+                      int *__restrict__ flags, unsigned long long *__restrict__ covered)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    for ( int64_t A = warp0; A < nnode; A += nwarps ) {
+        int eq[3], nfree = 0, rfirst = 0, bad = 0;
+#pragma unroll
+        for ( int i = 0; i < 3; i++ ) {
+            eq[i] = nodeeq[A * 3 + i];
+            if ( eq[i] < 0 || eq[i] > neq ) { bad = 1; eq[i] = 0; }
+            if ( eq[i] ) {
+                if ( eqnode[eq[i] - 1] != (int32_t)( A * 4 + i ) ) bad = 1;      // an equation shared by two dofs
+                if ( rfirst && eq[i] != rfirst + nfree ) bad = 1;                // not consecutive
+                if ( !rfirst ) rfirst = eq[i];
+                nfree++;
+            }
+        }
+        if ( !rfirst ) {
+            if ( bad && lane == 0 ) atomicOr(flags, 1);
+            continue;
+        }
+        const int p0 = rowptr[rfirst - 1], len = rowptr[rfirst] - p0;
+        // all rows of the node have the same columns
+        for ( int i = 0; i < 3; i++ ) {
+            if ( !eq[i] || eq[i] == rfirst ) continue;
+            const int p = rowptr[eq[i] - 1];
+            if ( rowptr[eq[i]] - p != len ) { bad = 1; continue; }
+            for ( int t = lane; t < len; t += 32 ) if ( colind[p + t] != colind[p0 + t] ) bad = 1;
+        }
+        // number of column blocks
+        int nb = 0, carry = -1;
+        for ( int t0 = 0; t0 < len; t0 += 32 ) {
+            const int t = t0 + lane;
+            const int node = t < len ? ( eqnode[colind[p0 + t]] >> 2 ) : -2;
+            if ( node == -1 ) bad = 1;                   // a column that is no dof of this element set
+            int prev = __shfl_up_sync(0xffffffffu, node, 1);
+            if ( lane == 0 ) prev = carry;
+            nb += __popc(__ballot_sync(0xffffffffu, t < len && node != prev));
+            carry = __shfl_sync(0xffffffffu, node, 31);
+        }
+        // every block the elements around the node produce is in the row
+        const int v0 = ninc_start[A], nv = ninc_start[A + 1] - v0;
+        for ( int it = lane; it < nv * 4; it += 32 ) {
+            const int ea = ninc[v0 + ( it >> 2 )];
+            const int B = conn[(int64_t)( ea >> 3 ) * 4 + ( it & 3 )] - 1;
+            int cB = 0;
+#pragma unroll
+            for ( int j = 2; j >= 0; j-- ) if ( nodeeq[(int64_t) B * 3 + j] > 0 ) cB = nodeeq[(int64_t) B * 3 + j];
+            if ( cB ) {
+                int lo = p0, hi = p0 + len - 1, found = 0;
+                while ( lo <= hi ) {
+                    const int mid = ( lo + hi ) >> 1, v = colind[mid];
+                    if ( v == cB - 1 ) { found = 1; break; }
+                    if ( v < cB - 1 ) lo = mid + 1; else hi = mid - 1;
+                }
+                if ( !found ) bad = 1;
+            }
+        }
+        if ( __any_sync(0xffffffffu, bad) && lane == 0 ) atomicOr(flags, 1);
+        if ( lane == 0 ) {
+            if ( nb > kTetMaxBlk ) atomicOr(flags + 1, 1);
+            atomicAdd(covered, (unsigned long long) nfree * (unsigned long long) len);
+        }
+    }
+}
+
+// gradients, volume and volume-weighted Lame constants of every element
+__global__ void __launch_bounds__(128)
+tet_geometry_kernel(ElemSetView S, int64_t nelem, double *__restrict__ rec)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride ) {
+        double g[4][3], c[12];
+#pragma unroll
+        for ( int a = 0; a < 4; a++ ) {
+            const int node = S.conn[e * 4 + a] - 1;
+#pragma unroll
+            for ( int j = 0; j < 3; j++ ) c[3 * a + j] = S.coords[(int64_t) node * 3 + j];
+        }
+        const double dV = fabs(tet_dNdx(c, g)) * ( 1.0 / 6.0 );
+        const MatParams mp = S.mat[S.matid[e]];
+        double lam, mu;
+        isole_lame(mp.E, mp.nu, lam, mu);
+        double2 *o = reinterpret_cast< double2 * >( rec + e * kTetRec );
+#pragma unroll
+        for ( int a = 0; a < 2; a++ ) {
+            o[3 * a] = make_double2(g[2 * a][0], g[2 * a][1]);
+            o[3 * a + 1] = make_double2(g[2 * a][2], g[2 * a + 1][0]);
+            o[3 * a + 2] = make_double2(g[2 * a + 1][1], g[2 * a + 1][2]);
+        }
+        o[6] = make_double2(dV * lam, dV * mu);
+        o[7] = make_double2(dV, 0.0);
+    }
+}
+
+// material tangent of every element's Gauss point (sets with a MisesMat)
+__global__ void __launch_bounds__(128)
+tet_tangent_kernel(ElemSetView S, int64_t nelem, double *__restrict__ Dout)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride ) {
+        const MatParams mp = S.mat[S.matid[e]];
+        double D[36];
+        if ( mp.type == (double) OB200_MAT_MISES ) mises_tangent(mp, &S.state[e], D);
+        else isole_D(mp.E, mp.nu, D);
+#pragma unroll
+        for ( int i = 0; i < 36; i++ ) Dout[e * 36 + i] = D[i];
+    }
+}
+
+struct TetRowsView {
+    int64_t nnode;
+    const int32_t *ninc_start, *ninc, *conn, *nodeeq, *eqnode, *rowptr, *colind;
+    const double *rec, *D;
+};
+
+template< int MODE >        // bit 0: add to val (else overwrite), bit 1: general 6x6 tangent per element (else isotropic)
+__global__ void __launch_bounds__(kTetWarps * 32)
+ltrspace_rows_kernel(TetRowsView V, double *__restrict__ val)
+{
+    constexpr bool ACCUM = ( MODE & 1 ) != 0, GEN = ( MODE & 2 ) != 0;
+    __shared__ int4 s_conn[kTetWarps][32];
+    __shared__ int s_ea[kTetWarps][32];
+    __shared__ int s_blk[kTetWarps][kTetMaxBlk];
+    __shared__ unsigned short s_off[kTetWarps][kTetMaxBlk];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t) gridDim.x * kTetWarps;
+    for ( int64_t A = (int64_t) blockIdx.x * kTetWarps + w; A < V.nnode; A += nwarps ) {
+        int eqA[3];
+#pragma unroll
+        for ( int i = 0; i < 3; i++ ) eqA[i] = V.nodeeq[A * 3 + i];
+        const int rfirst = eqA[0] ? eqA[0] : eqA[1] ? eqA[1] : eqA[2];
+        if ( !rfirst ) continue;
+        const int p0 = V.rowptr[rfirst - 1], len = V.rowptr[rfirst] - p0;
+        // the column blocks of the node: runs of entries that belong to one column node
+        int nb = 0, carry = -1;
+        for ( int t0 = 0; t0 < len; t0 += 32 ) {
+            const int t = t0 + lane;
+            const int node = t < len ? ( V.eqnode[V.colind[p0 + t]] >> 2 ) : -2;
+            int prev = __shfl_up_sync(0xffffffffu, node, 1);
+            if ( lane == 0 ) prev = carry;
+            const bool start = t < len && node != prev;
+            const unsigned m = __ballot_sync(0xffffffffu, start);
+            if ( start ) {
+                const int idx = nb + __popc(m & ( ( 1u << lane ) - 1u ));
+                if ( idx < kTetMaxBlk ) {
+                    s_blk[w][idx] = node;
+                    s_off[w][idx] = (unsigned short) t;
+                }
+            }
+            nb += __popc(m);
+            carry = __shfl_sync(0xffffffffu, node, 31);
+        }
+        if ( nb > kTetMaxBlk ) nb = kTetMaxBlk;          // tet_bind declines such a matrix
+        __syncwarp();
+        const int v0 = V.ninc_start[A], nv = V.ninc_start[A + 1] - v0;
+        for ( int bb = 0; bb < nb; bb += 32 ) {
+            const bool active = bb + lane < nb;
+            const int B = active ? s_blk[w][bb + lane] : -1;
+            double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            for ( int vb = 0; vb < nv; vb += 32 ) {
+                if ( vb + lane < nv ) {
+                    const int ea = V.ninc[v0 + vb + lane];
+                    s_ea[w][lane] = ea;
+                    s_conn[w][lane] = reinterpret_cast< const int4 * >( V.conn )[ea >> 3];
+                }
+                __syncwarp();
+                const int n = min(32, nv - vb);
+                for ( int k = 0; k < n; k++ ) {          // ascending element number
+                    const int4 cn = s_conn[w][k];
+                    const int b = cn.x - 1 == B ? 0 : cn.y - 1 == B ? 1 : cn.z - 1 == B ? 2 : cn.w - 1 == B ? 3 : -1;
+                    if ( b >= 0 ) {
+                        const int ea = s_ea[w][k];
+                        const int64_t e = ea >> 3;
+                        const double *rec = V.rec + e * kTetRec;
+                        const int a = ea & 7;
+                        const double ga[3] = { rec[3 * a], rec[3 * a + 1], rec[3 * a + 2] };
+                        const double gb[3] = { rec[3 * b], rec[3 * b + 1], rec[3 * b + 2] };
+                        if ( GEN ) block_general(acc, ga, gb, V.D + e * 36, rec[14]);
+                        else block_iso(acc, ga, gb, rec[12], rec[13]);
+                    }
+                }
+                __syncwarp();
+            }
+            if ( active ) {
+                const int off = s_off[w][bb + lane];
+                const bool fb[3] = { V.nodeeq[(int64_t) B * 3] > 0, V.nodeeq[(int64_t) B * 3 + 1] > 0, V.nodeeq[(int64_t) B * 3 + 2] > 0 };
+#pragma unroll
+                for ( int i = 0; i < 3; i++ ) {
+                    if ( !eqA[i] ) continue;
+                    double *o = val + V.rowptr[eqA[i] - 1] + off;
+                    int jj = 0;
+#pragma unroll
+                    for ( int j = 0; j < 3; j++ )
+                        if ( fb[j] ) {
+                            if ( ACCUM ) o[jj] += acc[3 * i + j];
+                            else o[jj] = acc[3 * i + j];
+                            jj++;
+                        }
+                }
+            }
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+
+int tet_bind(ob200_elemset *S, ob200_csr *A)
+{
+    ob200_context *ctx = S->ctx;
+    S->rows_ok = false;
+    if ( getenv("OB200_ASSEMBLY") && !strcmp(getenv("OB200_ASSEMBLY"), "slotmap") ) return OB200_OK;      // generic path (cross-checks)
+    if ( S->etype != OB200_LTRSPACE || S->nelem == 0 || !S->ninc.p || A->neq == 0 || A->neq != S->neq ) return OB200_OK;
+    if ( A->maxrow > 0xFFFF ) return OB200_OK;
+    OB_CHECK( S->eqnode.alloc(A->neq) );
+    OB_CUDA( cudaMemsetAsync(S->eqnode.p, 0xFF, sizeof( int32_t ) * (size_t) A->neq, ctx->stream) );
+    OB_LAUNCH(ctx, tet_eqnode_kernel, ctx->shape.grid(S->nnode * 3, 256, 8), 256, 0, S->nnode, S->nodeeq.p, S->eqnode.p);
+    DevBuf< int > flags;
+    OB_CHECK( flags.alloc(4) );            // [0] mismatch, [1] capacity, [2..3] 64-bit count of covered entries
+    OB_CUDA( cudaMemsetAsync(flags.p, 0, sizeof( int ) * 4, ctx->stream) );
+    OB_LAUNCH(ctx, tet_rows_check_kernel, ctx->shape.grid(S->nnode * 32, 256, 8), 256, 0, S->nnode, S->ninc_start.p, S->ninc.p,
+              S->conn.p, S->nodeeq.p, S->eqnode.p, A->rowptr.p, A->colind.p, A->neq, flags.p,
+              reinterpret_cast< unsigned long long * >( flags.p + 2 ));
+    int h[4] = { 0, 0, 0, 0 };
+    OB_CUDA( cudaMemcpyAsync(h, flags.p, sizeof( int ) * 4, cudaMemcpyDeviceToHost, ctx->stream) );
+    OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+    S->rows_ok = ( h[0] == 0 && h[1] == 0 );
+    unsigned long long cov;
+    memcpy(&cov, h + 2, sizeof( cov ));
+    S->covers_all = ( (int64_t) cov == A->nnz );
+    if ( S->rows_ok && !S->trec.p ) {
+        OB_CHECK( S->trec.alloc(S->nelem * kTetRec) );
+        OB_LAUNCH(ctx, tet_geometry_kernel, ctx->shape.grid(S->nelem, 128, 8), 128, 0, S->view(), S->nelem, S->trec.p);
+    }
+    return OB200_OK;
+}
+
+int tet_assemble_ltrspace(ob200_elemset *S, ob200_csr *A)
+{
+    ob200_context *ctx = S->ctx;
+    const bool gen = !S->all_isole;
+    if ( gen ) {
+        if ( !S->tangent.p ) OB_CHECK( S->tangent.alloc(S->nelem * 36) );
+        OB_LAUNCH(ctx, tet_tangent_kernel, ctx->shape.grid(S->nelem, 128, 8), 128, 0, S->view(), S->nelem, S->tangent.p);
+    }
+    TetRowsView V{ S->nnode, S->ninc_start.p, S->ninc.p, S->conn.p, S->nodeeq.p, S->eqnode.p, A->rowptr.p, A->colind.p, S->trec.p,
+                   S->tangent.p };
+    const int grid = ctx->shape.grid(S->nnode * 32, kTetWarps * 32, 8);
+    if ( A->zero_pending && !S->covers_all ) OB_CHECK( ob200_csr_materialize(A) );
+    const bool accum = !A->zero_pending;           // else every entry of the pattern is written once: the pending zero() is absorbed
+    if ( gen ) {
+        if ( accum ) OB_LAUNCH(ctx, ltrspace_rows_kernel< 3 >, grid, kTetWarps * 32, 0, V, A->val.p);
+        else OB_LAUNCH(ctx, ltrspace_rows_kernel< 2 >, grid, kTetWarps * 32, 0, V, A->val.p);
+    } else {
+        if ( accum ) OB_LAUNCH(ctx, ltrspace_rows_kernel< 1 >, grid, kTetWarps * 32, 0, V, A->val.p);
+        else OB_LAUNCH(ctx, ltrspace_rows_kernel< 0 >, grid, kTetWarps * 32, 0, V, A->val.p);
+    }
+    A->zero_pending = false;
+    return OB200_OK;
+}
+
+} // namespace ob200

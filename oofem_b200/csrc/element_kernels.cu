@@ -444,7 +444,8 @@ static int sched_key(ob200_elemset *S, unsigned long long key[8])
     const char *env = getenv("OB200_ASSEMBLY");
     key[5] = ( (unsigned long long) S->etype << 56 ) ^ ( (unsigned long long) S->nnode << 28 ) ^ (unsigned long long) S->nelem;
     key[6] = ( (unsigned long long) (unsigned int) S->neq << 32 ) ^ (unsigned long long) S->nmat;
-    key[7] = env ? ( !strcmp(env, "gather") ? 1 : 2 ) : 0;
+    key[7] = 0;
+    for ( const char *c = env; c && *c; c++ ) key[7] = key[7] * 131 + (unsigned char) *c;          // the mode decides which schedule is built
     return OB200_OK;
 }
 
@@ -601,7 +602,12 @@ int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
     OB_REQUIRE(S && Ke, OB200_EINVAL, "elemset_stiffness: null argument");
     StagedOut< double > o;
     OB_CHECK( o.stage(S->ctx, Ke, S->nelem * S->nd * S->nd, on_device) );
-    OB_CHECK( launch_stiffness(S, OUT_KE, o.d, nullptr, nullptr) );
+    // LSpace: the FP64 tensor-path kernel of the strip assembly (assemble_strips.cu); OB200_KE=dfma keeps the lane-per-block kernel
+    const char *ke = getenv("OB200_KE");
+    if ( S->etype == OB200_LSPACE && !( ke && !strcmp(ke, "dfma") ) && ( reinterpret_cast< uintptr_t >( o.d ) & 15 ) == 0 )
+        OB_CHECK( strips_element_matrices(S, o.d) );
+    else
+        OB_CHECK( launch_stiffness(S, OUT_KE, o.d, nullptr, nullptr) );
     return o.finish(S->ctx);
 }
 
@@ -655,7 +661,8 @@ int ob200_elemset_bind(ob200_elemset *S, ob200_csr *A)
         // preferred: owner-computes assembly (no atomics); its preparation also verifies that the
         // matrix pattern is the one of this element set
         OB_CHECK( gather_bind(S, A) );
-        if ( !S->gather_ok ) OB_CHECK( build_slot_map(S, A) );
+        if ( !S->gather_ok && !S->strips_ok ) OB_CHECK( tet_bind(S, A) );
+        if ( !S->gather_ok && !S->strips_ok && !S->rows_ok ) OB_CHECK( build_slot_map(S, A) );
         S->have_bind = true;
         S->bind_structure = A->structure_version;
     }
@@ -671,6 +678,16 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
     if ( S->bound != A || S->bound_version != A->structure_version ) OB_CHECK( ob200_elemset_bind(S, A) );
     if ( S->gather_ok ) {
         if ( S->nelem ) OB_CHECK( S->cluster_ok ? cluster_assemble_lspace(S, A) : gather_assemble_lspace(S, A) );
+        ob200_csr_touch(A);
+        return OB200_OK;
+    }
+    if ( S->strips_ok ) {
+        if ( S->nelem ) OB_CHECK( strips_assemble_lspace(S, A) );
+        ob200_csr_touch(A);
+        return OB200_OK;
+    }
+    if ( S->rows_ok ) {
+        if ( S->nelem ) OB_CHECK( tet_assemble_ltrspace(S, A) );
         ob200_csr_touch(A);
         return OB200_OK;
     }

@@ -80,6 +80,11 @@ struct ob200_sched {
     ob200::DevBuf< unsigned char > ebidx, nloc, npar, cl_recs, cl_steps;
     ob200::DevBuf< unsigned short > nbase;
     ob200::DevBuf< int32_t > cnodes, ncl, cl_begin, cl_step;
+    // node-row assembly of LTRSpace (assemble_tet.cu): equation -> (node, component), per-element gradients / volume / Lame
+    bool rows_ok = false;
+    bool strips_ok = false;                        // LSpace with a general tangent: element strips (assemble_strips.cu) on the node-block schedule
+    ob200::DevBuf< int32_t > eqnode;
+    ob200::DevBuf< double > trec;
 };
 
 struct ob200_elemset : ob200_sched {
@@ -89,6 +94,8 @@ struct ob200_elemset : ob200_sched {
     int32_t nmat = 0, neq = 0;
     bool has_state = false;
     ob200::DevBuf< double > coords, mat, state;
+    ob200::DevBuf< double > tangent;               // [nelem][36] material tangents of the LTRSpace node-row assembly (sets with a MisesMat)
+    ob200::DevBuf< double > kebuf;                 // [nelem][24][24] element matrices of the strip assembly
     ob200::DevBuf< int32_t > conn, matid, loc;
     ob200_csr *bound = nullptr;
     int64_t bound_version = -1;
@@ -122,4 +129,8 @@ int gather_bind(ob200_elemset *S, ob200_csr *A);                 // at bind: blo
 int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A);      // the kernel
 int cluster_bind(ob200_elemset *S, ob200_csr *A);                // assemble_cluster.cu: cluster schedule (after gather_bind)
 int cluster_assemble_lspace(ob200_elemset *S, ob200_csr *A);     // assemble_cluster.cu: the kernel
+int tet_bind(ob200_elemset *S, ob200_csr *A);                    // assemble_tet.cu: checks of the LTRSpace node-row assembly
+int tet_assemble_ltrspace(ob200_elemset *S, ob200_csr *A);       // assemble_tet.cu: the kernel
+int strips_element_matrices(ob200_elemset *S, double *Ke);       // assemble_strips.cu: LSpace element matrices, general tangent (FP64 DMMA)
+int strips_assemble_lspace(ob200_elemset *S, ob200_csr *A);      // assemble_strips.cu: element matrices + rows from strips
 }

@@ -96,6 +96,10 @@ class ElementSet:
         check(lib().ob200_elemset_get_state(self.h, ptr(st), 0))
         return st
 
+    def setState(self, st):
+        st = np.ascontiguousarray(st, dtype=np.float64)
+        check(lib().ob200_elemset_set_state(self.h, ptr(st), 0))
+
     def close(self):
         if self.h:
             lib().ob200_elemset_destroy(self.h)

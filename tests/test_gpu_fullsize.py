@@ -79,6 +79,20 @@ def test_three_assembly_algorithms_agree_at_1m_hex(ctx, beam, monkeypatch):
     assert float((vg - vs).abs().max()) / scale < 1e-13
 
 
+def test_strip_assembly_agrees_with_cluster_assembly_at_1m_hex(ctx, beam, monkeypatch):
+    """The general-tangent path (element matrices on the FP64 tensor path + rows from strips, assemble_strips.cu -- the one a
+    MisesMat set takes) forced onto the linear benchmark mesh (OB200_ASSEMBLY=strips) against the cluster kernel."""
+    import torch
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(beam["loc"], beam["neq"])
+    vc = _assemble(ctx, beam, A, "cluster", monkeypatch, "lspace_cluster_kernel")
+    vs = _assemble(ctx, beam, A, "strips", monkeypatch, "lspace_rows_kernel")
+    scale = float(vc.abs().max())
+    assert float((vc - vs).abs().max()) / scale < 1e-13
+    vs2 = _assemble(ctx, beam, A, "strips", monkeypatch, "lspace_ke_dmma_kernel")
+    assert torch.equal(vs, vs2), "strip assembly is not bit-reproducible run to run"
+
+
 def test_blocked_spmv_vs_csr_spmv_and_cg_variants_at_1m_hex(ctx, beam, monkeypatch):
     import torch
     monkeypatch.delenv("OB200_ASSEMBLY", raising=False)

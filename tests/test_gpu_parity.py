@@ -239,6 +239,91 @@ def test_mises_material_point_vs_oracle(ctx, etype):
     assert relerr(A.times(x), orc.compcol_times(md.colptr, md.rowind, val_cc, x)) < TOL_KE
 
 
+@pytest.mark.parametrize("etype,mat,kernels", [
+    ("lspace", "mises", ("lspace_ke_dmma_kernel", "lspace_rows_kernel")),
+    ("ltrspace", "mises", ("tet_tangent_kernel", "ltrspace_rows_kernel")),
+    ("ltrspace", "isole", ("ltrspace_rows_kernel",)),
+])
+def test_owner_computes_general_tangent(ctx, etype, mat, kernels, monkeypatch):
+    """MisesMat tangents (LSpace: element strips, assemble_strips.cu; LTRSpace: node rows, assemble_tet.cu) and the linear
+    LTRSpace assemble without atomics and without the slot map: the kernels that ran are the owner-computes ones, the values
+    agree with the oracle and with the slot-map path on the same material state, a second assembly accumulates, and the
+    result is bit-identical run to run.  Irregular node / element numbering, two materials."""
+    monkeypatch.delenv("OB200_ASSEMBLY", raising=False)
+    m0 = (Material("misesmat", 210e3, 0.3, sig0=240.0, H=2100.0, omega_crit=0.2, a=30.0) if mat == "mises"
+          else Material("isole", 210e3, 0.3))
+    pb = _random_problem(etype, 7, 4, 3, seed=21, mat=m0)
+    rng = np.random.default_rng(17)
+    nnode, nelem = pb.coords.shape[0], pb.conn.shape[0]
+    perm = rng.permutation(nnode)
+    coords = np.empty_like(pb.coords)
+    coords[perm] = pb.coords
+    pb.coords, pb.conn = coords, np.ascontiguousarray((perm[pb.conn - 1] + 1).astype(np.int32)[rng.permutation(nelem)])
+    for bc in pb.bcs:
+        bc.nodes = perm[bc.nodes - 1] + 1
+    for ld in pb.loads:
+        ld.nodes = perm[ld.nodes - 1] + 1
+    pb.materials = [m0, Material("isole", 70e3, 0.2)]
+    pb.elem_mat = rng.integers(0, 2, size=nelem).astype(np.int32)
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    if mat == "mises":                                       # a plastic, uncommitted increment: unsymmetric tangents
+        u = rng.normal(size=pb.coords.shape) * 6e-3
+        dom.elems.giveInternalForcesVector(u)
+        orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams,
+                                  u[pb.conn - 1].reshape(nelem, -1), md.state)
+        Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, md.state)
+        assert np.abs(Ke_o - Ke_o.transpose(0, 2, 1)).max() > 0.0
+    else:
+        Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams)
+    assert relerr(dom.elems.computeStiffnessMatrix(), Ke_o) < TOL_KE
+    val_o = orc.compcol_assemble(md.loc, Ke_o, md.colptr, md.rowind)          # column storage of K = row storage of K^T
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    x = rng.normal(size=dom.neq)
+    y_o = orc.compcol_times(md.colptr, md.rowind, val_o, x)
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    A.zero()
+    dom.elems.assembleStiffness(A)
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    for k in kernels:
+        assert any(n.startswith(k) for n in prof), (k, sorted(prof))
+    assert not any(n.startswith(("slot_map_kernel", "lspace_stiffness_kernel", "ltrspace_stiffness_kernel")) for n in prof), sorted(prof)
+    v1 = A.values().copy()
+    assert relerr(A.times(x), y_o) < TOL_KE
+    A.zero()
+    dom.elems.assembleStiffness(A)
+    assert np.array_equal(A.values(), v1), "owner-computes assembly is not bit-reproducible run to run"
+    dom.elems.assembleStiffness(A)                           # no zero(): SparseMtrx::assemble adds
+    assert relerr(A.values(), 2.0 * v1) < 1e-15
+    # the generic slot-map / atomic path on the same state
+    monkeypatch.setenv("OB200_ASSEMBLY", "slotmap")
+    dom2 = Domain(ctx, pb)
+    if mat == "mises":
+        dom2.elems.setState(dom.elems.state())
+    B = CudaCSR(ctx)
+    B.buildInternalStructure(dom2.loc, dom2.neq)
+    dom2.elems.assembleStiffness(B)
+    assert relerr(B.values(), v1) < 1e-13
+
+
+def test_lspace_element_matrix_kernels_agree(ctx, monkeypatch):
+    """The FP64 tensor-path element-matrix kernel (assemble_strips.cu) against the lane-per-block kernel (OB200_KE=dfma)."""
+    pb = _random_problem("lspace", 6, 4, 3, seed=4, mat=Material("isole", 210e3, 0.3))
+    dom = Domain(ctx, pb)
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    k1 = dom.elems.computeStiffnessMatrix()
+    monkeypatch.setenv("OB200_KE", "dfma")
+    k2 = dom.elems.computeStiffnessMatrix()
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    assert any(n.startswith("lspace_ke_dmma_kernel") for n in prof) and any(n.startswith("lspace_stiffness_kernel") for n in prof), sorted(prof)
+    assert relerr(k1, k2) < 1e-14
+
+
 def test_extrapolated_forces_vs_oracle(ctx):
     pb = _random_problem("lspace", 6, 3, 3, seed=9, mat=Material("isole", 70e3, 0.25))
     md = orc.Model(pb)
