@@ -1040,6 +1040,7 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
     memcpy(&cov, h + 2, sizeof( cov ));
     S->covers_all = ( (int64_t) cov == A->nnz );
     if ( S->gather_ok && !allpairs ) OB_CHECK( cluster_bind(S, A) );
+    if ( S->strips_ok ) OB_CHECK( strips_bind(S, A) );
     return OB200_OK;
 }
 

@@ -605,7 +605,7 @@ int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
     // LSpace: the FP64 tensor-path kernel of the strip assembly (assemble_strips.cu); OB200_KE=dfma keeps the lane-per-block kernel
     const char *ke = getenv("OB200_KE");
     if ( S->etype == OB200_LSPACE && !( ke && !strcmp(ke, "dfma") ) && ( reinterpret_cast< uintptr_t >( o.d ) & 15 ) == 0 )
-        OB_CHECK( strips_element_matrices(S, o.d) );
+        OB_CHECK( strips_element_matrices(S, o.d, nullptr) );
     else
         OB_CHECK( launch_stiffness(S, OUT_KE, o.d, nullptr, nullptr) );
     return o.finish(S->ctx);

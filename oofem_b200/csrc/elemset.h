@@ -85,6 +85,8 @@ struct ob200_sched {
     bool strips_ok = false;                        // LSpace with a general tangent: element strips (assemble_strips.cu) on the node-block schedule
     ob200::DevBuf< int32_t > eqnode;
     ob200::DevBuf< double > trec;
+    ob200::DevBuf< int32_t > row_tstart, row_desc, row_vis;             // strip assembly: per-node descriptors (two int4 per node) ...
+    ob200::DevBuf< unsigned char > row_vtab;                   // ... and column tables (576 B per chunk of eight incidences)
 };
 
 struct ob200_elemset : ob200_sched {
@@ -95,7 +97,7 @@ struct ob200_elemset : ob200_sched {
     bool has_state = false;
     ob200::DevBuf< double > coords, mat, state;
     ob200::DevBuf< double > tangent;               // [nelem][36] material tangents of the LTRSpace node-row assembly (sets with a MisesMat)
-    ob200::DevBuf< double > kebuf;                 // [nelem][24][24] element matrices of the strip assembly
+    ob200::DevBuf< double > kebuf;                 // [nvisit][3][24] element-matrix strips of the strip assembly, in incidence order
     ob200::DevBuf< int32_t > conn, matid, loc;
     ob200_csr *bound = nullptr;
     int64_t bound_version = -1;
@@ -131,6 +133,7 @@ int cluster_bind(ob200_elemset *S, ob200_csr *A);                // assemble_clu
 int cluster_assemble_lspace(ob200_elemset *S, ob200_csr *A);     // assemble_cluster.cu: the kernel
 int tet_bind(ob200_elemset *S, ob200_csr *A);                    // assemble_tet.cu: checks of the LTRSpace node-row assembly
 int tet_assemble_ltrspace(ob200_elemset *S, ob200_csr *A);       // assemble_tet.cu: the kernel
-int strips_element_matrices(ob200_elemset *S, double *Ke);       // assemble_strips.cu: LSpace element matrices, general tangent (FP64 DMMA)
+int strips_element_matrices(ob200_elemset *S, double *Ke, const int32_t *vis);       // assemble_strips.cu: LSpace element matrices, general tangent (FP64 DMMA)
+int strips_bind(ob200_elemset *S, ob200_csr *A);                 // assemble_strips.cu: per-node descriptors and column tables (after gather_bind)
 int strips_assemble_lspace(ob200_elemset *S, ob200_csr *A);      // assemble_strips.cu: element matrices + rows from strips
 }
