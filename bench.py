@@ -48,11 +48,11 @@ def load_peaks():
 # workload
 # ---------------------------------------------------------------------------------------
 
-def slab_problem(nx, ny, nz, rank, nranks):
+def slab_problem(nx, ny, nz, rank, nranks, etype="lspace"):
     """Local mesh of rank `rank`: slab [rank*nx, (rank+1)*nx] of a beam nranks*nx long
     (oofem_b200.partition.slab_partition), clamped at x = 0, with its own equation numbering."""
     from oofem_b200 import meshgen, partition
-    part = partition.slab_partition(nx, ny, nz, rank, nranks)
+    part = partition.slab_partition(nx, ny, nz, rank, nranks, etype=etype)
     fixed_mask = np.zeros((part.coords.shape[0], 3), dtype=bool)
     plane = (ny + 1) * (nz + 1)
     if rank == 0:
@@ -121,7 +121,10 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def workload_name(nx, ny, nz):
+def workload_name(nx, ny, nz, etype="lspace"):
+    if etype == "ltrspace":
+        return (f"synthetic structured {nx}x{ny}x{nz} cells x 6 = {6 * nx * ny * nz} LTRSpace tetrahedra, isotropic linear elastic "
+                f"cantilever per GPU, FP64 PCG (BASELINE.json configs[2])")
     return (f"synthetic structured {nx}x{ny}x{nz} = {nx * ny * nz} hex LSpace isotropic linear elastic "
             f"cantilever per GPU, FP64 PCG (BASELINE.json configs[1])")
 
@@ -303,7 +306,8 @@ def run_ours(args):
     if args.scaling == "strong":
         # the beam of --nx elements is cut into `world` x-slabs (a remainder of nx / world is dropped: say so in config)
         nx = max(1, args.nx // world)
-    pb = slab_problem(nx, ny, nz, rank, world)
+    etype = args.etype
+    pb = slab_problem(nx, ny, nz, rank, world, etype)
     nelem, neq = pb["conn"].shape[0], pb["neq"]
     matparams = np.array([[capi.MAT_ISOLE, 210e3, 0.3, 0, 0, 0, 0, 0]], dtype=np.float64)
     matid = np.zeros(nelem, np.int32)
@@ -312,7 +316,7 @@ def run_ours(args):
     t = lambda a: torch.as_tensor(a, device=dev)
     d_coords, d_conn, d_loc, d_matid = t(pb["coords"]), t(pb["conn"]), t(pb["loc"]), t(matid)
     torch.cuda.synchronize()
-    S = ElementSet(ctx, "lspace", d_coords, d_conn, d_matid, matparams, d_loc, neq)
+    S = ElementSet(ctx, etype, d_coords, d_conn, d_matid, matparams, d_loc, neq)
     A = CudaCSR(ctx)
     t0 = time.time()
     A.buildInternalStructure(d_loc, neq)
@@ -390,7 +394,7 @@ def run_ours(args):
 
     def step_e2e():
         t0 = time.perf_counter()
-        S2 = ElementSet(ctx, "lspace", h_coords, h_conn, h_matid, matparams, h_loc, neq)   # H2D of the mesh
+        S2 = ElementSet(ctx, etype, h_coords, h_conn, h_matid, matparams, h_loc, neq)      # H2D of the mesh
         A.zero()
         S2.assembleStiffness(A)                                                           # slot map + fused assembly
         ctx.sync()
@@ -451,7 +455,8 @@ def run_ours(args):
     blocked, nrb, nblk = int(layout[0]), int(layout[1]), int(layout[2])
     asm_name = next((k for k in ("lspace_cluster_kernel< false >", "lspace_cluster_kernel< true >",
                                  "lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
-                                 "lspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_cluster_kernel< false >")
+                                 "lspace_stiffness_kernel< OUT_CSR >", "ltrspace_rows_kernel< 0 >", "ltrspace_rows_kernel< 1 >",
+                                 "ltrspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_cluster_kernel< false >")
     ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
     ms_asmk, n_asmk = prof.get(asm_name, (0.0, 0))
     # algorithmic bytes: SpMV reads val (8 B) + colind (4 B) per non-zero, and per
@@ -465,20 +470,21 @@ def run_ours(args):
     spmv_gbs = spmv_bytes / spmv_dur / 1e9 if spmv_dur > 0 else 0.0
     # assembly: per element conn (32 B) + matid (4 B) + location array (96 B), coordinates once per node
     # (24 B), every matrix value written once (8 B per non-zero)
-    asm_bytes = nelem * (32.0 + 4.0 + 96.0) + pb["coords"].shape[0] * 24.0 + 8.0 * nnz
+    nen = pb["conn"].shape[1]
+    asm_bytes = nelem * (4.0 * nen + 4.0 + 12.0 * nen) + pb["coords"].shape[0] * 24.0 + 8.0 * nnz
     asm_dur = ms_asmk / max(n_asmk, 1) * 1e-3
     asm_gbs = asm_bytes / asm_dur / 1e9 if asm_dur > 0 else 0.0
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         traffic = {}
-    full_size = (nx, ny, nz) == (250, 64, 64)         # the captures were taken at this size
+    full_size = (nx, ny, nz) == (250, 64, 64) and etype == "lspace"         # the captures were taken at this size
     spmv_traffic = traffic.get(spmv_name.split("<")[0].strip()) if full_size else None
     asm_traffic = traffic.get(asm_name.split("<")[0].strip()) if full_size else None
     kernel_share = {k: round(v[0] / (t_step * args.steps) , 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and etype == "lspace":
         cpu = reference_sample((40, 20, 20), 20, 1, 0, 0)
         kind = "reference"
         if cpu is None:
@@ -492,9 +498,12 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
         "ms_assembly": t_asm, "ms_pcg": t_cg,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(nx, ny, nz) if args.scaling == "weak" else
-                               f"strong scaling: one {nx * world}x{ny}x{nz} = {nx * world * ny * nz} hex LSpace beam cut into {world} x-slabs "
-                               f"of {nx}x{ny}x{nz}, FP64 PCG (BASELINE.json configs[4] pattern at the configs[1] size)",
+        "config": {"workload": workload_name(nx, ny, nz, etype) if args.scaling == "weak" else
+                               (f"strong scaling: one {nx * world}x{ny}x{nz} = {nx * world * ny * nz} hex LSpace beam cut into {world} x-slabs "
+                                f"of {nx}x{ny}x{nz}, FP64 PCG (BASELINE.json configs[4] pattern at the configs[1] size)" if etype == "lspace" else
+                                f"one {nx * world}x{ny}x{nz}-cell beam = {6 * nx * world * ny * nz} LTRSpace tetrahedra, element-partitioned into "
+                                f"{world} x-slabs of {6 * nx * ny * nz}, isotropic linear elastic, FP64 PCG (BASELINE.json configs[2])"),
+                   "etype": etype,
                    "nelem_per_gpu": nelem, "neq_per_gpu": neq, "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
                    "precond": "diag", "partition": f"{world} x-slabs, shared-plane halo" if world > 1 else "none",
                    "transport": ("peer memory (CUDA IPC mailboxes over NVLink)" if comm.p2p else "NCCL") if comm else "none",
@@ -514,7 +523,8 @@ def run_ours(args):
                               "frac": asm_gbs / peak, "traffic": asm_traffic, "algorithmic_bytes_per_launch": asm_bytes,
                               "avg_launch_ms": asm_dur * 1e3, "launches": n_asmk,
                               "traffic_source": "profiles/traffic.json (committed ncu --set full capture at this size); not measured in this run",
-                              "note": "cluster assembly (assemble_cluster.cu): shared-memory / dependency-chain bound, see DESIGN.md 3.3"},
+                              "note": ("cluster assembly (assemble_cluster.cu): shared-memory / dependency-chain bound, see DESIGN.md 3.3"
+                                       if etype == "lspace" else "node-row assembly (assemble_tet.cu), see DESIGN.md 3.3b")},
         "kernel_time_share": kernel_share,
         "e2e": {"value": total_elems / e_asm, "unit": "elements/s", "pcg_iters_per_s": args.cg_iters / e_cg,
                 "h2d_bytes_per_step": int(h2d_asm + h2d_cg), "d2h_bytes_per_step": int(d2h_cg),
@@ -530,7 +540,7 @@ def run_ours(args):
                                 "cores": cpu.get("threads", 1), "kind": kind,
                                 "sample": f"{cpu['nelem']} LSpace elements (40x20x20 sample of the same beam) assembled by the "
                                           f"reference's EngngModel::assemble into CompCol; 20 IML CG iterations at nnz {cpu['nnz']}"}
-    if world == 1 and not args.no_e2e_executable and not args.no_cpu_baseline:
+    if world == 1 and not args.no_e2e_executable and not args.no_cpu_baseline and etype == "lspace":
         # OOFEM's own executable with the plugin against the unmodified reference executable, same generated input, to
         # convergence (outside every timed region above; wall-clock of whole processes)
         try:
@@ -561,6 +571,8 @@ def main():
     ap.add_argument("--ny", type=int, default=64)
     ap.add_argument("--nz", type=int, default=64)
     ap.add_argument("--cg-iters", type=int, default=50)
+    ap.add_argument("--etype", default="lspace", choices=["lspace", "ltrspace"],
+                    help="ltrspace: BASELINE configs[2] (every cell of the beam split into six tetrahedra); the default line is lspace")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --nx x ny x nz elements per GPU (default, the driver's contract); strong: --nx in total, cut into N slabs")
     ap.add_argument("--ref-sample-elems", type=int, default=32000, help="reference arm: elements assembled per timed step")

@@ -40,8 +40,16 @@
 
 namespace ob200 {
 
-constexpr int kClNodes = 64;                 // most nodes a cluster owns
-constexpr int kClBlocks = 1728;              // most 3x3 blocks (positions per plane) a cluster owns: 64 nodes x 27
+#ifndef OB200_CL_NODES
+#define OB200_CL_NODES 64
+#endif
+#ifndef OB200_CL_CTAS
+#define OB200_CL_CTAS 1
+#endif
+constexpr int kClNodes = OB200_CL_NODES;     // most nodes a cluster owns
+constexpr int kClBlocks = 27 * kClNodes;     // most 3x3 blocks (positions per plane) a cluster owns
+constexpr int kClCtas = OB200_CL_CTAS;       // CTAs per SM (two need clusters of 32 nodes and the small rings to fit shared memory)
+static_assert( kClNodes <= 64, "six bits of cluster-local node index in the flush table" );
 constexpr int kClMaxValence = 16;            // elements around a node
 constexpr int kClVisits = kClNodes * kClMaxValence;      // most (node, element) incidences of a cluster
 constexpr int kClMaxCell = 2048;             // most nodes in one spatial cell (beyond: the path declines)
@@ -74,7 +82,11 @@ constexpr int kClThreads = ( kCWarps + 1 + kGWarps ) * 32;
 constexpr int kRecSlots = OB200_CL_RECSLOTS;                // ring of record packets (4 elements each): deep enough to cover the HBM latency
 constexpr int kHSlots = OB200_CL_HSLOTS;                   // ring of gradient packets between the geometry and the contraction warps
 constexpr int kHStride = 200;                // doubles per element in the gradient ring: H[kstep][3a'+i][gp & 3], kstep stride 100
-constexpr int kBankCap = 120;                // positions per shared-memory bank residue (16 residues of 8-byte words)
+#ifndef OB200_CL_BANKCAP
+#define OB200_CL_BANKCAP ( OB200_CL_NODES == 64 ? 120 : ( 30 * OB200_CL_NODES ) / 16 )
+#endif
+constexpr int kBankCap = OB200_CL_BANKCAP;   // positions per shared-memory bank residue (16 residues of 8-byte words)
+static_assert( 16 * kBankCap <= 2048 && 16 * kBankCap > kClBlocks, "plane positions: 11 bits in the flush table" );
 constexpr int kPlane = 16 * kBankCap;        // plane stride: positions are handed out per bank residue (see cl_records_kernel)
 static_assert( kCWarps <= 16, "dependency bytes per record" );
 constexpr int kBuildThreads = 128;
@@ -854,7 +866,7 @@ struct ClWalk {
 };
 
 template< bool ACCUM >
-__global__ void __launch_bounds__(kClThreads, 1)
+__global__ void __launch_bounds__(kClThreads, kClCtas)
 lspace_cluster_kernel(ElemSetView S, ClView V, double *__restrict__ val)
 {
     extern __shared__ __align__(128) unsigned char cl_smem_raw[];
@@ -1236,7 +1248,7 @@ int cluster_assemble_lspace(ob200_elemset *S, ob200_csr *A)
     OB_CUDA( cudaFuncSetAttribute(lspace_cluster_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
     ClView V{ (const ClRecord *) S->cl_recs.p, (const ClBlob *) S->cl_steps.p, S->cl_step.p, S->nclusters };
     ElemSetView v = S->view();
-    int grid = ctx->shape.sms;                          // persistent: one CTA per SM
+    int grid = ctx->shape.sms * kClCtas;                // persistent: kClCtas CTAs per SM
     if ( grid > S->nclusters ) grid = S->nclusters;
     if ( A->zero_pending && !S->covers_all ) OB_CHECK( ob200_csr_materialize(A) );
     // error word: a failure of the previous launch is reported now (and by ob200_context_sync); no host synchronisation here

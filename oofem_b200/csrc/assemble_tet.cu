@@ -17,6 +17,8 @@
 // consecutive, every block an element produces is in the pattern); otherwise the slot-map path stays in use.
 #include "element_device.cuh"
 #include "elemset.h"
+#include "scan.cuh"
+#include <limits.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -248,6 +250,210 @@ ltrspace_rows_kernel(TetRowsView V, double *__restrict__ val)
     }
 }
 
+// ---- the fast path: per-node tables built once per bound matrix ------------------------------------------------
+//
+// Per node (two int4): d0 = { first incidence, elements around the node, byte offset of its table, column blocks },
+// d1 = { start of row 0 / 1 / 2 in val or -1 (prescribed), 0 }.  The table: per column block its first column << 3 | free-dof mask
+// (u16), then the start of every block's item list (u8 [nb + 1]), per item (incidence v, local node b) its column block or 0xFF
+// (u8 [4 nv]), and the items ordered by (block, incidence) (u8 [4 nv]).  With it the kernel has no search and no divergence: one lane
+// per (element, local node) item forms its 3x3 block and parks it in shared memory, then one lane per column block adds the parked
+// blocks of its list -- ascending element number, so the result is bit-reproducible -- and writes its columns.
+constexpr int kTet2Warps = 4;
+constexpr int kTet2MaxVal = 32;          // elements around a node
+constexpr int kTet2MaxBlk = 64;          // column blocks of a node's rows
+constexpr int kTet2Items = 4 * kTet2MaxVal;
+constexpr int kTet2TabMax = 2 * kTet2MaxBlk + ( kTet2MaxBlk + 1 ) + 2 * kTet2Items + 8;
+
+__device__ __forceinline__ int tet2_table_bytes(int nb, int nv)
+{
+    return ( ( 2 * nb + 3 ) & ~3 ) + ( ( nb + 1 + 8 * nv + 3 ) & ~3 );
+}
+
+template< bool FILL >
+__global__ void __launch_bounds__(256)
+tet_tables_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const int32_t *__restrict__ ninc,
+                  const int32_t *__restrict__ conn, const int32_t *__restrict__ nodeeq, const int32_t *__restrict__ eqnode,
+                  const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                  int32_t *__restrict__ tbytes, const int32_t *__restrict__ toff, int4 *__restrict__ rdesc, unsigned char *__restrict__ tab,
+                  int *__restrict__ flags)
+{
+    __shared__ int s_blk[8][kTet2MaxBlk];
+    __shared__ unsigned short s_pk[8][kTet2MaxBlk];
+    __shared__ unsigned char s_bidx[8][kTet2Items];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    for ( int64_t A = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5; A < nnode; A += nwarps ) {
+        int eqA[3];
+#pragma unroll
+        for ( int i = 0; i < 3; i++ ) eqA[i] = nodeeq[A * 3 + i];
+        const int rfirst = eqA[0] > 0 ? eqA[0] : eqA[1] > 0 ? eqA[1] : eqA[2] > 0 ? eqA[2] : 0;
+        const int v0 = ninc_start[A], nv = ninc_start[A + 1] - v0;
+        int nb = 0;
+        if ( rfirst ) {
+            const int p0 = rowptr[rfirst - 1], len = rowptr[rfirst] - p0;
+            int carry = -1;
+            for ( int t0 = 0; t0 < len; t0 += 32 ) {
+                const int t = t0 + lane;
+                const int node = t < len ? ( eqnode[colind[p0 + t]] >> 2 ) : -2;
+                int prev = __shfl_up_sync(0xffffffffu, node, 1);
+                if ( lane == 0 ) prev = carry;
+                const bool start = t < len && node != prev;
+                const unsigned m = __ballot_sync(0xffffffffu, start);
+                if ( start ) {
+                    const int idx = nb + __popc(m & ( ( 1u << lane ) - 1u ));
+                    if ( idx < kTet2MaxBlk ) {
+                        s_blk[w][idx] = node;
+                        const int cm = ( nodeeq[(int64_t) node * 3] > 0 ? 1 : 0 ) | ( nodeeq[(int64_t) node * 3 + 1] > 0 ? 2 : 0 ) |
+                                       ( nodeeq[(int64_t) node * 3 + 2] > 0 ? 4 : 0 );
+                        s_pk[w][idx] = (unsigned short)( ( t << 3 ) | cm );
+                    }
+                }
+                nb += __popc(m);
+                carry = __shfl_sync(0xffffffffu, node, 31);
+            }
+            if ( lane == 0 && ( nb > kTet2MaxBlk || nv > kTet2MaxVal || len >= 8192 ) ) atomicOr(flags, 1);      // beyond the fast path
+            if ( nb > kTet2MaxBlk ) nb = kTet2MaxBlk;
+        }
+        const int nvu = rfirst ? min(nv, kTet2MaxVal) : 0;
+        if ( !FILL ) {
+            if ( lane == 0 ) tbytes[A] = rfirst ? tet2_table_bytes(nb, nvu) : 0;
+            continue;
+        }
+        if ( lane == 0 ) {
+            rdesc[2 * A] = make_int4(v0, nvu, toff[A], rfirst ? nb : 0);
+            rdesc[2 * A + 1] = make_int4(eqA[0] > 0 ? rowptr[eqA[0] - 1] : -1, eqA[1] > 0 ? rowptr[eqA[1] - 1] : -1,
+                                         eqA[2] > 0 ? rowptr[eqA[2] - 1] : -1, 0);
+        }
+        if ( !rfirst ) continue;
+        __syncwarp();
+        unsigned char *T = tab + toff[A];
+        unsigned short *colpk = reinterpret_cast< unsigned short * >( T );
+        unsigned char *blkstart = T + ( ( 2 * nb + 3 ) & ~3 );
+        unsigned char *bidx = blkstart + nb + 1, *items = bidx + 4 * nvu;
+        for ( int B = lane; B < nb; B += 32 ) colpk[B] = s_pk[w][B];
+        // block of every item
+        for ( int it = lane; it < 4 * nvu; it += 32 ) {
+            const int ea = ninc[v0 + ( it >> 2 )];
+            const int Bn = conn[(int64_t)( ea >> 3 ) * 4 + ( it & 3 )] - 1;
+            int idx = 0xFF;
+            for ( int B = 0; B < nb; B++ )
+                if ( s_blk[w][B] == Bn ) idx = B;
+            s_bidx[w][it] = (unsigned char) idx;
+            bidx[it] = (unsigned char) idx;
+        }
+        __syncwarp();
+        // items ordered by (block, incidence): lane = block counts its items, a scan gives the starts, then it lists them
+        int run = 0;
+        for ( int b0 = 0; b0 < nb; b0 += 32 ) {
+            const int B = b0 + lane;
+            int cnt = 0;
+            if ( B < nb )
+                for ( int it = 0; it < 4 * nvu; it++ ) cnt += s_bidx[w][it] == B;
+            int incl = cnt;
+#pragma unroll
+            for ( int o = 1; o < 32; o <<= 1 ) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ( lane >= o ) incl += t;
+            }
+            int at = run + incl - cnt;
+            if ( B < nb ) {
+                blkstart[B] = (unsigned char) at;
+                for ( int it = 0; it < 4 * nvu; it++ )
+                    if ( s_bidx[w][it] == B ) items[at++] = (unsigned char) it;
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if ( lane == 0 ) blkstart[nb] = (unsigned char) run;
+        __syncwarp();
+    }
+}
+
+struct TetRows2View {
+    int64_t nnode;
+    const int4 *rdesc;
+    const unsigned char *tab;
+    const int32_t *ninc;
+    const double *rec, *D;
+};
+
+template< int MODE >        // bit 0: add to val (else overwrite), bit 1: general 6x6 tangent per element (else isotropic)
+__global__ void __launch_bounds__(kTet2Warps * 32)
+ltrspace_rows2_kernel(const __grid_constant__ TetRows2View V, double *__restrict__ val)
+{
+    constexpr bool ACCUM = ( MODE & 1 ) != 0, GEN = ( MODE & 2 ) != 0;
+    __shared__ double s_park[kTet2Warps][kTet2Items * 9];
+    __shared__ __align__(16) unsigned char s_tab[kTet2Warps][( kTet2TabMax + 15 ) & ~15];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t) gridDim.x * kTet2Warps;
+    int64_t A = (int64_t) blockIdx.x * kTet2Warps + w;
+    if ( A >= V.nnode ) return;
+    // the descriptor of the next node is requested one node ahead
+    int4 d0 = V.rdesc[2 * A], d1 = V.rdesc[2 * A + 1];
+    for ( ; A < V.nnode; A += nwarps ) {
+        const int4 c0 = d0, c1 = d1;
+        if ( A + nwarps < V.nnode ) {
+            d0 = V.rdesc[2 * ( A + nwarps )];
+            d1 = V.rdesc[2 * ( A + nwarps ) + 1];
+        }
+        const int v0 = c0.x, nv = c0.y, nb = c0.w;
+        if ( nb == 0 ) continue;
+        const int tbytes = tet2_table_bytes(nb, nv);
+        {   // the node's table into shared memory, its element list into registers
+            const uint32_t *src = reinterpret_cast< const uint32_t * >( V.tab + c0.z );
+            uint32_t *dst = reinterpret_cast< uint32_t * >( s_tab[w] );
+            for ( int t = lane; t < tbytes / 4; t += 32 ) dst[t] = src[t];
+        }
+        const int ea_l = lane < nv ? V.ninc[v0 + lane] : 0;
+        __syncwarp();
+        const unsigned short *colpk = reinterpret_cast< const unsigned short * >( s_tab[w] );
+        const unsigned char *blkstart = s_tab[w] + ( ( 2 * nb + 3 ) & ~3 );
+        const unsigned char *bidx = blkstart + nb + 1, *items = bidx + 4 * nv;
+        // one lane per (element, local node): K_ab = V B_a^T D B_b (Structural3DElement::computeBmatrixAt, structural3delement.C:63-86)
+        for ( int it = lane; it - lane < 4 * nv; it += 32 ) {
+            const int ea = __shfl_sync(0xffffffffu, ea_l, ( it >> 2 ) & 31);
+            if ( it >= 4 * nv || bidx[it] == 0xFF ) continue;
+            const int64_t e = ea >> 3;
+            const int a = ea & 7, b = it & 3;
+            const double *rec = V.rec + e * kTetRec;
+            const double ga[3] = { rec[3 * a], rec[3 * a + 1], rec[3 * a + 2] };
+            const double gb[3] = { rec[3 * b], rec[3 * b + 1], rec[3 * b + 2] };
+            double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            if ( GEN ) block_general(acc, ga, gb, V.D + e * 36, rec[14]);
+            else block_iso(acc, ga, gb, rec[12], rec[13]);
+            double *pk = s_park[w] + it * 9;
+#pragma unroll
+            for ( int k = 0; k < 9; k++ ) pk[k] = acc[k];
+        }
+        __syncwarp();
+        // one lane per column block: its items in ascending element number
+        for ( int B = lane; B < nb; B += 32 ) {
+            double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            const int k1 = blkstart[B + 1];
+            for ( int k = blkstart[B]; k < k1; k++ ) {
+                const double *pk = s_park[w] + (int) items[k] * 9;
+#pragma unroll
+                for ( int q = 0; q < 9; q++ ) acc[q] += pk[q];
+            }
+            const int pkc = colpk[B], cm = pkc & 7, off = pkc >> 3;
+            const int rb[3] = { c1.x, c1.y, c1.z };
+#pragma unroll
+            for ( int i = 0; i < 3; i++ ) {
+                if ( rb[i] < 0 ) continue;
+                double *o = val + rb[i] + off;
+                int jj = 0;
+#pragma unroll
+                for ( int j = 0; j < 3; j++ )
+                    if ( cm & ( 1 << j ) ) {
+                        if ( ACCUM ) o[jj] += acc[3 * i + j];
+                        else o[jj] = acc[3 * i + j];
+                        jj++;
+                    }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 
 int tet_bind(ob200_elemset *S, ob200_csr *A)
@@ -277,6 +483,33 @@ int tet_bind(ob200_elemset *S, ob200_csr *A)
         OB_CHECK( S->trec.alloc(S->nelem * kTetRec) );
         OB_LAUNCH(ctx, tet_geometry_kernel, ctx->shape.grid(S->nelem, 128, 8), 128, 0, S->view(), S->nelem, S->trec.p);
     }
+    // the per-node tables of the fast kernel; meshes beyond its capacity (valence, blocks per row) keep ltrspace_rows_kernel
+    S->tet_fast = false;
+    const char *tk = getenv("OB200_TET_ROWS");
+    if ( S->rows_ok && !( tk && !strcmp(tk, "search") ) ) {
+        DevBuf< int32_t > tbytes;
+        DevBuf< int64_t > s64;
+        OB_CHECK( tbytes.alloc(S->nnode + 1) );
+        OB_CHECK( s64.alloc(S->nnode + 1) );
+        OB_CHECK( S->row_tstart.alloc(S->nnode + 1) );
+        OB_CUDA( cudaMemsetAsync(tbytes.p, 0, sizeof( int32_t ) * ( S->nnode + 1 ), ctx->stream) );
+        OB_CUDA( cudaMemsetAsync(flags.p, 0, sizeof( int ) * 4, ctx->stream) );
+        const int grid = ctx->shape.grid(S->nnode * 32, 256, 8);
+        OB_LAUNCH(ctx, tet_tables_kernel< false >, grid, 256, 0, S->nnode, S->ninc_start.p, S->ninc.p, S->conn.p, S->nodeeq.p, S->eqnode.p,
+                  A->rowptr.p, A->colind.p, tbytes.p, (const int32_t *) nullptr, (int4 *) nullptr, (unsigned char *) nullptr, flags.p);
+        int64_t total = 0;
+        OB_CHECK( exclusive_scan(ctx, tbytes.p, s64.p, S->nnode + 1, &total) );
+        OB_CUDA( cudaMemcpyAsync(h, flags.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
+        OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+        if ( h[0] == 0 && total < (int64_t) INT_MAX ) {
+            OB_CHECK( narrow_i64_to_i32(ctx, s64.p, S->row_tstart.p, S->nnode + 1) );
+            OB_CHECK( S->row_desc.alloc(S->nnode * 2 * 4) );
+            OB_CHECK( S->row_vtab.alloc(total > 0 ? total : 4) );
+            OB_LAUNCH(ctx, tet_tables_kernel< true >, grid, 256, 0, S->nnode, S->ninc_start.p, S->ninc.p, S->conn.p, S->nodeeq.p, S->eqnode.p,
+                      A->rowptr.p, A->colind.p, tbytes.p, S->row_tstart.p, reinterpret_cast< int4 * >( S->row_desc.p ), S->row_vtab.p, flags.p);
+            S->tet_fast = true;
+        }
+    }
     return OB200_OK;
 }
 
@@ -287,6 +520,18 @@ int tet_assemble_ltrspace(ob200_elemset *S, ob200_csr *A)
     if ( gen ) {
         if ( !S->tangent.p ) OB_CHECK( S->tangent.alloc(S->nelem * 36) );
         OB_LAUNCH(ctx, tet_tangent_kernel, ctx->shape.grid(S->nelem, 128, 8), 128, 0, S->view(), S->nelem, S->tangent.p);
+    }
+    if ( A->zero_pending && !S->covers_all ) OB_CHECK( ob200_csr_materialize(A) );
+    if ( S->tet_fast ) {
+        TetRows2View V2{ S->nnode, reinterpret_cast< const int4 * >( S->row_desc.p ), S->row_vtab.p, S->ninc.p, S->trec.p, S->tangent.p };
+        const int grid2 = ctx->shape.grid(S->nnode * 32, kTet2Warps * 32, 16);
+        const int mode = ( A->zero_pending ? 0 : 1 ) | ( gen ? 2 : 0 );
+        if ( mode == 0 ) OB_LAUNCH(ctx, ltrspace_rows2_kernel< 0 >, grid2, kTet2Warps * 32, 0, V2, A->val.p);
+        else if ( mode == 1 ) OB_LAUNCH(ctx, ltrspace_rows2_kernel< 1 >, grid2, kTet2Warps * 32, 0, V2, A->val.p);
+        else if ( mode == 2 ) OB_LAUNCH(ctx, ltrspace_rows2_kernel< 2 >, grid2, kTet2Warps * 32, 0, V2, A->val.p);
+        else OB_LAUNCH(ctx, ltrspace_rows2_kernel< 3 >, grid2, kTet2Warps * 32, 0, V2, A->val.p);
+        A->zero_pending = false;
+        return OB200_OK;
     }
     TetRowsView V{ S->nnode, S->ninc_start.p, S->ninc.p, S->conn.p, S->nodeeq.p, S->eqnode.p, A->rowptr.p, A->colind.p, S->trec.p,
                    S->tangent.p };

@@ -444,8 +444,9 @@ static int sched_key(ob200_elemset *S, unsigned long long key[8])
     const char *env = getenv("OB200_ASSEMBLY");
     key[5] = ( (unsigned long long) S->etype << 56 ) ^ ( (unsigned long long) S->nnode << 28 ) ^ (unsigned long long) S->nelem;
     key[6] = ( (unsigned long long) (unsigned int) S->neq << 32 ) ^ (unsigned long long) S->nmat;
-    key[7] = 0;
-    for ( const char *c = env; c && *c; c++ ) key[7] = key[7] * 131 + (unsigned char) *c;          // the mode decides which schedule is built
+    key[7] = 0;                                                                                     // the modes decide which schedule is built
+    for ( const char *c = env; c && *c; c++ ) key[7] = key[7] * 131 + (unsigned char) *c;
+    for ( const char *c = getenv("OB200_TET_ROWS"); c && *c; c++ ) key[7] = key[7] * 137 + (unsigned char) *c;
     return OB200_OK;
 }
 

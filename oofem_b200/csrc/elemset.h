@@ -81,7 +81,7 @@ struct ob200_sched {
     ob200::DevBuf< unsigned short > nbase;
     ob200::DevBuf< int32_t > cnodes, ncl, cl_begin, cl_step;
     // node-row assembly of LTRSpace (assemble_tet.cu): equation -> (node, component), per-element gradients / volume / Lame
-    bool rows_ok = false;
+    bool rows_ok = false, tet_fast = false;        // tet_fast: the table-driven kernel (per-node tables in row_desc / row_vtab)
     bool strips_ok = false;                        // LSpace with a general tangent: element strips (assemble_strips.cu) on the node-block schedule
     ob200::DevBuf< int32_t > eqnode;
     ob200::DevBuf< double > trec;

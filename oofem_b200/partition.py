@@ -58,13 +58,14 @@ def partition_mesh(coords: np.ndarray, conn: np.ndarray, elem_part: np.ndarray, 
     return LocalPartition(rank, nranks, coords[node_global].copy(), lconn, mine, node_global, shared, owner)
 
 
-def slab_partition(nx: int, ny: int, nz: int, rank: int, nranks: int, h: float = None) -> LocalPartition:
+def slab_partition(nx: int, ny: int, nz: int, rank: int, nranks: int, h: float = None, etype: str = "lspace") -> LocalPartition:
     """x-slab `rank` of a structured LSpace beam nranks*nx elements long, built locally (no global
     mesh is ever materialised -- this is what bench.py uses at 1M elements per GPU).  Identical to
     partition_mesh(hex_beam(nranks*nx, ny, nz), element x-index // nx, rank) -- tested."""
     if h is None:
         h = 1.0 / ny
-    coords, conn = meshgen.hex_beam(nx, ny, nz, nx * h, ny * h, nz * h)
+    gen = meshgen.hex_beam if etype == "lspace" else meshgen.tet_beam       # tet_beam: six tetrahedra per cell, cell-major
+    coords, conn = gen(nx, ny, nz, nx * h, ny * h, nz * h)
     coords[:, 0] += rank * nx * h
     plane = (ny + 1) * (nz + 1)
     nloc = coords.shape[0]
@@ -76,7 +77,7 @@ def slab_partition(nx: int, ny: int, nz: int, rank: int, nranks: int, h: float =
         owner[:plane] = rank - 1
     if rank < nranks - 1:
         shared[rank + 1] = np.arange(nloc - plane, nloc, dtype=np.int64)
-    elem_global = np.arange(conn.shape[0], dtype=np.int64) + rank * nx * ny * nz
+    elem_global = np.arange(conn.shape[0], dtype=np.int64) + rank * conn.shape[0]
     return LocalPartition(rank, nranks, coords, conn, elem_global, node_global, shared, owner)
 
 

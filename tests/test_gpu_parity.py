@@ -239,17 +239,23 @@ def test_mises_material_point_vs_oracle(ctx, etype):
     assert relerr(A.times(x), orc.compcol_times(md.colptr, md.rowind, val_cc, x)) < TOL_KE
 
 
-@pytest.mark.parametrize("etype,mat,kernels", [
-    ("lspace", "mises", ("lspace_ke_dmma_kernel", "lspace_rows_kernel")),
-    ("ltrspace", "mises", ("tet_tangent_kernel", "ltrspace_rows_kernel")),
-    ("ltrspace", "isole", ("ltrspace_rows_kernel",)),
+@pytest.mark.parametrize("etype,mat,kernels,tet_rows", [
+    ("lspace", "mises", ("lspace_ke_dmma_kernel", "lspace_rows_kernel"), None),
+    ("ltrspace", "mises", ("tet_tangent_kernel", "ltrspace_rows2_kernel"), None),
+    ("ltrspace", "isole", ("ltrspace_rows2_kernel",), None),
+    ("ltrspace", "mises", ("tet_tangent_kernel", "ltrspace_rows_kernel"), "search"),       # the kernel for meshes beyond the tables' capacity
+    ("ltrspace", "isole", ("ltrspace_rows_kernel",), "search"),
 ])
-def test_owner_computes_general_tangent(ctx, etype, mat, kernels, monkeypatch):
+def test_owner_computes_general_tangent(ctx, etype, mat, kernels, tet_rows, monkeypatch):
     """MisesMat tangents (LSpace: element strips, assemble_strips.cu; LTRSpace: node rows, assemble_tet.cu) and the linear
     LTRSpace assemble without atomics and without the slot map: the kernels that ran are the owner-computes ones, the values
     agree with the oracle and with the slot-map path on the same material state, a second assembly accumulates, and the
     result is bit-identical run to run.  Irregular node / element numbering, two materials."""
     monkeypatch.delenv("OB200_ASSEMBLY", raising=False)
+    if tet_rows:
+        monkeypatch.setenv("OB200_TET_ROWS", tet_rows)
+    else:
+        monkeypatch.delenv("OB200_TET_ROWS", raising=False)
     m0 = (Material("misesmat", 210e3, 0.3, sig0=240.0, H=2100.0, omega_crit=0.2, a=30.0) if mat == "mises"
           else Material("isole", 210e3, 0.3))
     pb = _random_problem(etype, 7, 4, 3, seed=21, mat=m0)

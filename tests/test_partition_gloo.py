@@ -178,3 +178,26 @@ def test_halo_arrays_shapes_single_rank():
     nodeeq, neq = meshgen.equation_numbers(part.coords.shape[0], np.zeros((part.coords.shape[0], 3), bool))
     neigh, offs, eqs, owned = partition.halo_arrays(part, nodeeq, neq)
     assert neigh.size == 0 and offs.tolist() == [0] and eqs.size == 0 and owned.all()
+
+
+def test_tet_slab_partition_matches_partition_of_global_mesh():
+    """bench.py --etype ltrspace builds every rank's slab of tetrahedra locally: identical to cutting the global tet_beam by
+    the cell's x-index (BASELINE configs[2], element partition a la oofem2part)."""
+    nx, ny, nz, world = 3, 2, 2, 3
+    h = 1.0 / ny
+    coords_g, conn_g = meshgen.tet_beam(world * nx, ny, nz, world * nx * h, ny * h, nz * h)
+    per = 6 * nx * ny * nz
+    # tet_beam numbers the six tetrahedra of a cell consecutively?  derive the owner from the element centroid instead
+    cx = coords_g[conn_g - 1][:, :, 0].mean(axis=1)
+    epart = np.minimum((cx / (nx * h)).astype(np.int32), world - 1)
+    for rank in range(world):
+        part = partition.partition_mesh(coords_g, conn_g, epart, rank, world)
+        slab = partition.slab_partition(nx, ny, nz, rank, world, etype="ltrspace")
+        assert slab.conn.shape == (per, 4) and np.array_equal(slab.node_global, part.node_global)
+        assert np.allclose(slab.coords, part.coords, atol=1e-14)
+        key = lambda c: np.sort(np.sort(c, axis=1).view([("", c.dtype)] * 4).ravel())
+        assert np.array_equal(key(slab.conn), key(part.conn))           # the same tetrahedra (the local order may differ)
+        assert np.array_equal(slab.node_owner, part.node_owner)
+        assert sorted(slab.shared_nodes) == sorted(part.shared_nodes)
+        for r in part.shared_nodes:
+            assert np.array_equal(slab.shared_nodes[r], part.shared_nodes[r])
