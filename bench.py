@@ -455,7 +455,8 @@ def run_ours(args):
     blocked, nrb, nblk = int(layout[0]), int(layout[1]), int(layout[2])
     asm_name = next((k for k in ("lspace_cluster_kernel< false >", "lspace_cluster_kernel< true >",
                                  "lspace_gather_kernel< false >", "lspace_gather_kernel< true >",
-                                 "lspace_stiffness_kernel< OUT_CSR >", "ltrspace_rows_kernel< 0 >", "ltrspace_rows_kernel< 1 >",
+                                 "lspace_stiffness_kernel< OUT_CSR >", "ltrspace_rows2_kernel< 0 >", "ltrspace_rows2_kernel< 1 >",
+                                 "ltrspace_rows_kernel< 0 >", "ltrspace_rows_kernel< 1 >",
                                  "ltrspace_stiffness_kernel< OUT_CSR >") if k in prof), "lspace_cluster_kernel< false >")
     ms_spmv, n_spmv = prof.get(spmv_name, (0.0, 0))
     ms_asmk, n_asmk = prof.get(asm_name, (0.0, 0))
