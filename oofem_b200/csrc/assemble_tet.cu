@@ -254,19 +254,27 @@ ltrspace_rows_kernel(TetRowsView V, double *__restrict__ val)
 //
 // Per node (two int4): d0 = { first incidence, elements around the node, byte offset of its table, column blocks },
 // d1 = { start of row 0 / 1 / 2 in val or -1 (prescribed), 0 }.  The table: per column block its first column << 3 | free-dof mask
-// (u16), then the start of every block's item list (u8 [nb + 1]), per item (incidence v, local node b) its column block or 0xFF
+// (u16), the units -- a column block's items in runs of at most kTet2Unit: start of every unit's item list (u8 [nu + 1]) and its block |
+// first-unit-of-its-block << 6 | block-has-several-units << 7 (u8 [nu]) --, per item (incidence v, local node b) its column block or 0xFF
 // (u8 [4 nv]), and the items ordered by (block, incidence) (u8 [4 nv]).  With it the kernel has no search and no divergence: one lane
-// per (element, local node) item forms its 3x3 block and parks it in shared memory, then one lane per column block adds the parked
-// blocks of its list -- ascending element number, so the result is bit-reproducible -- and writes its columns.
+// per (element, local node) item forms its 3x3 block and parks it in shared memory, then one lane per unit adds the parked blocks of
+// its list in ascending element number (with kTet2Unit = all items a unit is a whole column block).  The order of every sum is
+// fixed by the tables: bit-reproducible run to run.
 constexpr int kTet2Warps = 4;
 constexpr int kTet2MaxVal = 32;          // elements around a node
 constexpr int kTet2MaxBlk = 64;          // column blocks of a node's rows
 constexpr int kTet2Items = 4 * kTet2MaxVal;
-constexpr int kTet2TabMax = 2 * kTet2MaxBlk + ( kTet2MaxBlk + 1 ) + 2 * kTet2Items + 8;
+constexpr int kTet2Unit = kTet2Items;   // items one lane adds.  Measured (scripts/sweep_tet.sh): cutting the long lists (the diagonal block has one item per
+                                        // element around the node) into units of 8 shared by several lanes is slower, 1.96 vs 1.72 ms; so is staging
+                                        // the element records in shared memory (1.97 ms).  The tables keep the unit format.
+constexpr int kTet2MaxUnits = kTet2MaxBlk + kTet2Items / kTet2Unit;
+constexpr int kTet2TabMax = 2 * kTet2MaxBlk + ( 2 * kTet2MaxUnits + 1 ) + 2 * kTet2Items + 8;
 
+// most units of a node: one per block + one per kTet2Unit items
+__device__ __forceinline__ int tet2_max_units(int nb, int nv) { return nb + ( 4 * nv ) / kTet2Unit; }
 __device__ __forceinline__ int tet2_table_bytes(int nb, int nv)
 {
-    return ( ( 2 * nb + 3 ) & ~3 ) + ( ( nb + 1 + 8 * nv + 3 ) & ~3 );
+    return ( ( 2 * nb + 3 ) & ~3 ) + ( ( 2 * tet2_max_units(nb, nv) + 1 + 8 * nv + 3 ) & ~3 );
 }
 
 template< bool FILL >
@@ -319,17 +327,19 @@ tet_tables_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const i
             if ( lane == 0 ) tbytes[A] = rfirst ? tet2_table_bytes(nb, nvu) : 0;
             continue;
         }
-        if ( lane == 0 ) {
-            rdesc[2 * A] = make_int4(v0, nvu, toff[A], rfirst ? nb : 0);
-            rdesc[2 * A + 1] = make_int4(eqA[0] > 0 ? rowptr[eqA[0] - 1] : -1, eqA[1] > 0 ? rowptr[eqA[1] - 1] : -1,
-                                         eqA[2] > 0 ? rowptr[eqA[2] - 1] : -1, 0);
+        if ( !rfirst ) {
+            if ( lane == 0 ) {
+                rdesc[2 * A] = make_int4(v0, 0, 0, 0);
+                rdesc[2 * A + 1] = make_int4(-1, -1, -1, 0);
+            }
+            continue;
         }
-        if ( !rfirst ) continue;
         __syncwarp();
         unsigned char *T = tab + toff[A];
         unsigned short *colpk = reinterpret_cast< unsigned short * >( T );
-        unsigned char *blkstart = T + ( ( 2 * nb + 3 ) & ~3 );
-        unsigned char *bidx = blkstart + nb + 1, *items = bidx + 4 * nvu;
+        const int numax = tet2_max_units(nb, nvu);
+        unsigned char *ustart = T + ( ( 2 * nb + 3 ) & ~3 );
+        unsigned char *ublk = ustart + numax + 1, *bidx = ublk + numax, *items = bidx + 4 * nvu;
         for ( int B = lane; B < nb; B += 32 ) colpk[B] = s_pk[w][B];
         // block of every item
         for ( int it = lane; it < 4 * nvu; it += 32 ) {
@@ -342,28 +352,39 @@ tet_tables_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const i
             bidx[it] = (unsigned char) idx;
         }
         __syncwarp();
-        // items ordered by (block, incidence): lane = block counts its items, a scan gives the starts, then it lists them
-        int run = 0;
+        // items ordered by (block, incidence), cut into units: lane = block counts its items, scans give the starts, then it lists them
+        int run = 0, urun = 0;
         for ( int b0 = 0; b0 < nb; b0 += 32 ) {
             const int B = b0 + lane;
             int cnt = 0;
             if ( B < nb )
                 for ( int it = 0; it < 4 * nvu; it++ ) cnt += s_bidx[w][it] == B;
-            int incl = cnt;
+            const int nun = B < nb ? max(1, ( cnt + kTet2Unit - 1 ) / kTet2Unit) : 0;
+            int incl = cnt, uincl = nun;
 #pragma unroll
             for ( int o = 1; o < 32; o <<= 1 ) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if ( lane >= o ) incl += t;
+                const int t = __shfl_up_sync(0xffffffffu, incl, o), tu = __shfl_up_sync(0xffffffffu, uincl, o);
+                if ( lane >= o ) { incl += t; uincl += tu; }
             }
             int at = run + incl - cnt;
+            const int ut = urun + uincl - nun;
             if ( B < nb ) {
-                blkstart[B] = (unsigned char) at;
+                for ( int k = 0; k < nun; k++ ) {
+                    ustart[ut + k] = (unsigned char)( at + k * kTet2Unit );
+                    ublk[ut + k] = (unsigned char)( B | ( k == 0 ? 0x40 : 0 ) | ( nun > 1 ? 0x80 : 0 ) );
+                }
                 for ( int it = 0; it < 4 * nvu; it++ )
                     if ( s_bidx[w][it] == B ) items[at++] = (unsigned char) it;
             }
             run += __shfl_sync(0xffffffffu, incl, 31);
+            urun += __shfl_sync(0xffffffffu, uincl, 31);
         }
-        if ( lane == 0 ) blkstart[nb] = (unsigned char) run;
+        if ( lane == 0 ) {
+            ustart[urun] = (unsigned char) run;
+            rdesc[2 * A] = make_int4(v0, nvu, toff[A], nb);
+            rdesc[2 * A + 1] = make_int4(eqA[0] > 0 ? rowptr[eqA[0] - 1] : -1, eqA[1] > 0 ? rowptr[eqA[1] - 1] : -1,
+                                         eqA[2] > 0 ? rowptr[eqA[2] - 1] : -1, urun);
+        }
         __syncwarp();
     }
 }
@@ -406,8 +427,9 @@ ltrspace_rows2_kernel(const __grid_constant__ TetRows2View V, double *__restrict
         const int ea_l = lane < nv ? V.ninc[v0 + lane] : 0;
         __syncwarp();
         const unsigned short *colpk = reinterpret_cast< const unsigned short * >( s_tab[w] );
-        const unsigned char *blkstart = s_tab[w] + ( ( 2 * nb + 3 ) & ~3 );
-        const unsigned char *bidx = blkstart + nb + 1, *items = bidx + 4 * nv;
+        const int nu = c1.w, numax = tet2_max_units(nb, nv);
+        const unsigned char *ustart = s_tab[w] + ( ( 2 * nb + 3 ) & ~3 );
+        const unsigned char *ublk = ustart + numax + 1, *bidx = ublk + numax, *items = bidx + 4 * nv;
         // one lane per (element, local node): K_ab = V B_a^T D B_b (Structural3DElement::computeBmatrixAt, structural3delement.C:63-86)
         for ( int it = lane; it - lane < 4 * nv; it += 32 ) {
             const int ea = __shfl_sync(0xffffffffu, ea_l, ( it >> 2 ) & 31);
@@ -425,15 +447,7 @@ ltrspace_rows2_kernel(const __grid_constant__ TetRows2View V, double *__restrict
             for ( int k = 0; k < 9; k++ ) pk[k] = acc[k];
         }
         __syncwarp();
-        // one lane per column block: its items in ascending element number
-        for ( int B = lane; B < nb; B += 32 ) {
-            double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-            const int k1 = blkstart[B + 1];
-            for ( int k = blkstart[B]; k < k1; k++ ) {
-                const double *pk = s_park[w] + (int) items[k] * 9;
-#pragma unroll
-                for ( int q = 0; q < 9; q++ ) acc[q] += pk[q];
-            }
+        auto write_block = [&](int B, const double ( &acc )[9]) {
             const int pkc = colpk[B], cm = pkc & 7, off = pkc >> 3;
             const int rb[3] = { c1.x, c1.y, c1.z };
 #pragma unroll
@@ -449,6 +463,17 @@ ltrspace_rows2_kernel(const __grid_constant__ TetRows2View V, double *__restrict
                         jj++;
                     }
             }
+        };
+        // one lane per unit (= column block, see kTet2Unit): its items in ascending element number
+        for ( int u = lane; u < nu; u += 32 ) {
+            double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            const int k0 = ustart[u], k1 = ustart[u + 1];
+            for ( int k = k0; k < k1; k++ ) {
+                const double *pk = s_park[w] + (int) items[k] * 9;
+#pragma unroll
+                for ( int q = 0; q < 9; q++ ) acc[q] += pk[q];
+            }
+            write_block(ublk[u] & 0x3F, acc);
         }
         __syncwarp();
     }
