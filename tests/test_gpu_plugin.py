@@ -164,21 +164,28 @@ def test_stock_executable_mises_output_matches_reference_executable(name, tmp_pa
     assert np.abs(eo - er).max() <= 2e-5 * np.abs(er).max()
 
 
-@pytest.mark.parametrize("name,hooked", [("deadweight02", True), ("patch300", True), ("Mises01", False)])
+@pytest.mark.parametrize("name,hooked", [("deadweight02", True), ("patch300", True), ("patch301", True), ("Mises01", False),
+                                         ("interface3d", None), ("InterfaceEL_SurfQuad1", None)])
 def test_reference_own_tests_sm_through_the_plugin(name, hooked, tmp_path):
     """The reference's own tests/sm inputs (copied unchanged to tests/golden/ref_sm) with `lstype 9 smtype 11`: their
     #%BEGIN_CHECK% blocks are checked by the reference's errorcheck module inside the run (a mismatch is an OOFEM_ERROR and
-    a non-zero exit).  deadweight02 (LSpace, dead weight, nodes with single prescribed dofs) and patch300 (LTRSpace) take
-    the hooks; Mises01 is a truss1d model with both ends prescribed (no equation): host loops only."""
+    a non-zero exit).  deadweight02 (LSpace, dead weight, nodes with single prescribed dofs), patch300 and patch301 (LTRSpace)
+    take the hooks; Mises01 is a truss1d model with both ends prescribed (no equation): host loops only.  hooked = None: models the
+    batched hooks must DECLINE -- LTRSpace / LSpace mixed with interface elements (interface3d, a LinearStatic;
+    InterfaceEL_SurfQuad1) -- so that every element matrix reaches the cudacsr matrix through SparseMtrx::assemble(loc, mat) and
+    cudacg solves.  (brick_nlgeo_1 and tutorialmaterial, also LSpace-only inputs of tests/sm, have no free dof: nothing to solve.)"""
     need(EXE)
     lines = open(os.path.join(GOLDEN, "ref_sm", name + ".in")).read().splitlines()
-    k = next(i for i, l in enumerate(lines) if l.lower().startswith("staticstructural"))
-    lines[k] = lines[k].replace(" nmodules", " lstype 9 smtype 11 lstol 1e-14 lsiter 20000 lsprecond 1 nmodules")
+    k = next(i for i, l in enumerate(lines) if l.lower().startswith(("staticstructural", "linearstatic")))
+    lines[k] = lines[k].replace(" nmodules", " lstype 9 smtype 11 lstol 1e-14 lsiter 20000 lsprecond 1 nmodules", 1)
     fn = tmp_path / (name + ".in")
     fn.write_text("\n".join(lines) + "\n")
     r = subprocess.run([EXE, "-f", str(fn)], capture_output=True, text=True, cwd=tmp_path, timeout=600)
     log = r.stdout + r.stderr
     assert r.returncode == 0 and "Checking rules" in log and "Total 0 error(s)" in log, log[-3000:]
+    if hooked is None:
+        assert "CudaCG" in log and "batched tangent assembly on the GPU" not in log, log[-3000:]
+        return
     assert ("CudaCG" in log) == hooked          # Mises01 has no free dof: nothing to solve, the check values still hold
     assert ("batched tangent assembly on the GPU" in log) == hooked, log[-3000:]
     assert ("batched internal forces on the GPU" in log) == hooked, log[-3000:]
