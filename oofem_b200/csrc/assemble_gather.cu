@@ -77,6 +77,25 @@ __global__ void node_incidence_fill_kernel(const int32_t *__restrict__ conn, int
 
 // sort each node's visits (ascending element number): the accumulation order must not depend on
 // the order in which the atomics above happened to land
+// vis[element * 8 + local node] = position of that incidence in the (sorted) node -> element lists
+__global__ void visit_index_kernel(const int32_t *__restrict__ ninc, int64_t nvisit, int32_t *__restrict__ vis)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; p < nvisit; p += stride ) vis[ninc[p]] = (int32_t) p;
+}
+
+// eqcount[eq - 1] += 1 for every free nodal dof: an equation that belongs to two nodal dofs (master / slave) rules out the
+// owner-computes vector assembly
+__global__ void equation_owner_count_kernel(const int32_t *__restrict__ nodeeq, int64_t n, int32_t neq, int32_t *__restrict__ eqcount, int *__restrict__ bad)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) {
+        const int eq = nodeeq[t];
+        if ( eq > neq ) atomicOr(bad, 1);
+        else if ( eq > 0 && atomicAdd(eqcount + eq - 1, 1) > 0 ) atomicOr(bad, 1);
+    }
+}
+
 __global__ void node_incidence_sort_kernel(int64_t nnode, const int32_t *__restrict__ start, int32_t *__restrict__ ninc)
 {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
@@ -983,6 +1002,19 @@ int gather_prepare_mesh(ob200_elemset *S)
     OB_CUDA( cudaMemsetAsync(S->nodeeq.p, 0, sizeof( int32_t ) * (size_t) S->nnode * 3, ctx->stream) );
     OB_CHECK( elemset_await_loc(S) );
     OB_LAUNCH(ctx, node_equations_kernel, grid, 256, 0, S->conn.p, S->loc.p, S->nelem, S->nen, S->nodeeq.p);
+    // position of every (element, local node) incidence in the node lists (strip assembly, owner-computes vector assembly)
+    OB_CHECK( S->row_vis.alloc(S->nelem * 8) );
+    OB_LAUNCH(ctx, visit_index_kernel, grid, 256, 0, S->ninc.p, n, S->row_vis.p);
+    {
+        DevBuf< int32_t > eqcount;
+        OB_CHECK( eqcount.alloc(S->neq > 0 ? S->neq : 1) );
+        OB_CUDA( cudaMemsetAsync(eqcount.p, 0, sizeof( int32_t ) * (size_t)( S->neq > 0 ? S->neq : 1 ), ctx->stream) );
+        OB_CUDA( cudaMemsetAsync(bad.p, 0, sizeof( int ), ctx->stream) );
+        OB_LAUNCH(ctx, equation_owner_count_kernel, ctx->shape.grid(S->nnode * 3, 256, 8), 256, 0, S->nodeeq.p, S->nnode * 3, S->neq, eqcount.p, bad.p);
+        OB_CUDA( cudaMemcpyAsync(&hbad, bad.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) );
+        OB_CUDA( cudaStreamSynchronize(ctx->stream) );
+        S->eq_unique = ( hbad == 0 );
+    }
     if ( S->etype != OB200_LSPACE ) return OB200_OK;          // the rest is the visit-group schedule of the LSpace kernels
     OB_CHECK( S->ninc_node.alloc(n) );
     S->ngroups = (int32_t)( ( S->nvisit - 1 ) / kGroupVisits + 1 );

@@ -235,13 +235,6 @@ struct RowsView {
     const double *Ke;               // strips in incidence order: [nvisit][3][24]
 };
 
-// vis[element * 8 + local node] = position of that incidence in the node -> element lists
-__global__ void rows_visit_index_kernel(const int32_t *__restrict__ ninc, int64_t nvisit, int32_t *__restrict__ vis)
-{
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for ( int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; p < nvisit; p += stride ) vis[ninc[p]] = (int32_t) p;
-}
-
 // the tables: one warp per node; FILL = false counts the chunks of the node only
 template< bool FILL >
 __global__ void __launch_bounds__(kRowWarps * 32)
@@ -432,8 +425,6 @@ int strips_bind(ob200_elemset *S, ob200_csr *A)
     OB_CHECK( S->row_desc.alloc(S->nnode * 2 * 4) );
     OB_CHECK( S->row_vtab.alloc(( total > 0 ? total : 1 ) * kChunkBytes) );
     OB_CUDA( cudaMemsetAsync(S->row_vtab.p, 0xFF, (size_t)( total > 0 ? total : 1 ) * kChunkBytes, ctx->stream) );
-    OB_CHECK( S->row_vis.alloc(S->nvisit) );
-    OB_LAUNCH(ctx, rows_visit_index_kernel, ctx->shape.grid(S->nvisit, 256, 8), 256, 0, S->ninc.p, S->nvisit, S->row_vis.p);
     OB_LAUNCH(ctx, rows_tables_kernel< true >, grid, kRowWarps * 32, 0, S->nnode, S->ninc_start.p, S->ninc.p, S->nodeeq.p, A->rowptr.p,
               S->ebidx.p, S->nblk.p, S->blk.p, S->maxblk, nchunk.p, S->row_tstart.p, reinterpret_cast< int4 * >( S->row_desc.p ), S->row_vtab.p);
     return OB200_OK;

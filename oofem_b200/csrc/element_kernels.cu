@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kHexWarps * 32)
 lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
                               double *__restrict__ fglob, double *__restrict__ gp_strain,
                               double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
+                              double *__restrict__ fvis, const int32_t *__restrict__ vis,
                               int64_t e_begin, int64_t e_end)
 {
     __shared__ HexShared sh[kHexWarps];
@@ -167,6 +168,7 @@ lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, doubl
             }
             ebe += f * f;
             if ( fe ) fe[e * 24 + lane] = f;
+            if ( fvis ) fvis[(int64_t) vis[e * 8 + k] * 3 + c] = f;        // owner-computes assembly: node_force_gather_kernel adds them up
             if ( fglob ) {
                 int32_t r = S.loc[e * 24 + lane];
                 if ( r > 0 ) atomicAdd(fglob + r - 1, f);
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(128)
 ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
                                 double *__restrict__ fglob, double *__restrict__ gp_strain,
                                 double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
+                                double *__restrict__ fvis, const int32_t *__restrict__ vis,
                                 int64_t e_begin, int64_t e_end)
 {
     double ebe[3] = { 0.0, 0.0, 0.0 };
@@ -312,6 +315,7 @@ ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, dou
             for ( int i = 0; i < 3; i++ ) {
                 ebe[i] += fk[i] * fk[i];
                 if ( fe ) fe[e * 12 + 3 * a + i] = fk[i];
+                if ( fvis ) fvis[(int64_t) vis[e * 8 + a] * 3 + i] = fk[i];
                 if ( fglob ) {
                     int32_t r = S.loc[e * 12 + 3 * a + i];
                     if ( r > 0 ) atomicAdd(fglob + r - 1, fk[i]);
@@ -328,6 +332,71 @@ ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, dou
             if ( ( threadIdx.x & 31 ) == 0 && v != 0.0 ) atomicAdd(ebe_norm2 + c, v);
         }
     }
+}
+
+// Owner-computes vector assembly (EngngModel::assembleVectorFromElements, engngm.C:1351-, without atomics): one thread per
+// node adds the nodal forces of the elements around it in ascending element number -- fvis holds them in incidence order, so a
+// node reads 24 nv contiguous bytes -- into the node's free equations, and the squares of all of them per dof id
+// (the element-by-element norms of engngm.C:1108-1133).  The block sums are added in block order by norm_finish_kernel: the
+// whole result is bit-reproducible run to run.
+constexpr int kForceGatherThreads = 256;
+__global__ void __launch_bounds__(kForceGatherThreads)
+node_force_gather_kernel(int64_t nnode, const int32_t *__restrict__ ninc_start, const int32_t *__restrict__ nodeeq,
+                         const double *__restrict__ fvis, double *__restrict__ f, double *__restrict__ partial)
+{
+    __shared__ double s_red[kForceGatherThreads / 32][3];
+    const int64_t A = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    double sq[3] = { 0.0, 0.0, 0.0 };
+    if ( A < nnode ) {
+        const int v0 = ninc_start[A], v1 = ninc_start[A + 1];
+        double acc[3] = { 0.0, 0.0, 0.0 };
+        for ( int v = v0; v < v1; v++ ) {
+#pragma unroll
+            for ( int i = 0; i < 3; i++ ) {
+                const double x = fvis[(int64_t) v * 3 + i];
+                acc[i] += x;
+                sq[i] += x * x;
+            }
+        }
+#pragma unroll
+        for ( int i = 0; i < 3; i++ ) {
+            const int eq = nodeeq[A * 3 + i];
+            if ( eq > 0 && v1 > v0 ) f[eq - 1] += acc[i];
+        }
+    }
+    if ( !partial ) return;
+#pragma unroll
+    for ( int i = 0; i < 3; i++ ) {
+#pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+        if ( ( threadIdx.x & 31 ) == 0 ) s_red[threadIdx.x >> 5][i] = sq[i];
+    }
+    __syncthreads();
+    if ( threadIdx.x < 3 ) {
+        double t = 0.0;
+        for ( int w = 0; w < kForceGatherThreads / 32; w++ ) t += s_red[w][threadIdx.x];
+        partial[(int64_t) blockIdx.x * 3 + threadIdx.x] = t;
+    }
+}
+
+// out[c] = sum over blocks of partial[block][c], one block, fixed order
+__global__ void __launch_bounds__(256) norm_finish_kernel(const double *__restrict__ partial, int64_t nblocks, double *__restrict__ out)
+{
+    __shared__ double s_red[256][3];
+    double t[3] = { 0.0, 0.0, 0.0 };
+    for ( int64_t b = threadIdx.x; b < nblocks; b += 256 )
+#pragma unroll
+        for ( int i = 0; i < 3; i++ ) t[i] += partial[b * 3 + i];
+#pragma unroll
+    for ( int i = 0; i < 3; i++ ) s_red[threadIdx.x][i] = t[i];
+    __syncthreads();
+    for ( int o = 128; o > 0; o >>= 1 ) {
+        if ( (int) threadIdx.x < o )
+#pragma unroll
+            for ( int i = 0; i < 3; i++ ) s_red[threadIdx.x][i] += s_red[threadIdx.x + o][i];
+        __syncthreads();
+    }
+    if ( threadIdx.x < 3 ) out[threadIdx.x] = s_red[0][threadIdx.x];
 }
 
 // MaterialStatus::updateYourself: temp -> committed
@@ -395,12 +464,31 @@ static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe,
     ob200_context *ctx = S->ctx;
     ElemSetView v = S->view();
     if ( S->nelem == 0 ) return OB200_OK;
+    // assembly into the global vector: owner-computes (no atomics) when the node incidence is there and no equation belongs to two
+    // nodal dofs; OB200_VECTOR_ASSEMBLY=atomic keeps the scatter with atomicAdd (cross-check)
+    const char *va = getenv("OB200_VECTOR_ASSEMBLY");
+    const bool gather = fglob && S->eq_unique && S->row_vis.p && S->ninc_start.p && !( va && !strcmp(va, "atomic") );
+    double *fvis = nullptr;
+    if ( gather ) {
+        if ( !S->fvis.p ) OB_CHECK( S->fvis.alloc(S->nvisit * 3) );
+        fvis = S->fvis.p;
+    }
     if ( S->etype == OB200_LSPACE ) {
         int grid = ctx->shape.grid(S->nelem * 32, kHexWarps * 32, 4);
-        OB_LAUNCH(ctx, lspace_internal_forces_kernel, grid, kHexWarps * 32, 0, v, u, fe, fglob, eps, sig, ebe, 0, S->nelem);
+        OB_LAUNCH(ctx, lspace_internal_forces_kernel, grid, kHexWarps * 32, 0, v, u, fe, gather ? nullptr : fglob, eps, sig,
+                  gather ? nullptr : ebe, fvis, S->row_vis.p, 0, S->nelem);
     } else {
         int grid = ctx->shape.grid(S->nelem, 128, 8);
-        OB_LAUNCH(ctx, ltrspace_internal_forces_kernel, grid, 128, 0, v, u, fe, fglob, eps, sig, ebe, 0, S->nelem);
+        OB_LAUNCH(ctx, ltrspace_internal_forces_kernel, grid, 128, 0, v, u, fe, gather ? nullptr : fglob, eps, sig,
+                  gather ? nullptr : ebe, fvis, S->row_vis.p, 0, S->nelem);
+    }
+    if ( gather ) {
+        const int64_t nblocks = ( S->nnode + kForceGatherThreads - 1 ) / kForceGatherThreads;
+        DevBuf< double > partial;
+        if ( ebe ) OB_CHECK( partial.alloc(nblocks * 3) );
+        OB_LAUNCH(ctx, node_force_gather_kernel, (int) nblocks, kForceGatherThreads, 0, S->nnode, S->ninc_start.p, S->nodeeq.p, fvis, fglob,
+                  ebe ? partial.p : nullptr);
+        if ( ebe ) OB_LAUNCH(ctx, norm_finish_kernel, 1, 256, 0, partial.p, nblocks, ebe);
     }
     return OB200_OK;
 }

@@ -67,6 +67,8 @@ struct ob200_sched {
     int32_t maxval = 0;                            // largest number of elements around a node
     int64_t nvisit = 0;                            // nelem * nen
     ob200::DevBuf< int32_t > ninc_start, ninc, ninc_node, nodeeq;
+    ob200::DevBuf< int32_t > row_vis;              // [nelem][8]: position of the (element, local node) incidence in ninc
+    bool eq_unique = false;                        // no equation belongs to two nodal dofs: vectors can be assembled owner-computes
     // ... and what depends on the bound matrix
     bool gather_ok = false, covers_all = false;
     int32_t maxblk = 0, ngroups = 0;
@@ -85,7 +87,7 @@ struct ob200_sched {
     bool strips_ok = false;                        // LSpace with a general tangent: element strips (assemble_strips.cu) on the node-block schedule
     ob200::DevBuf< int32_t > eqnode;
     ob200::DevBuf< double > trec;
-    ob200::DevBuf< int32_t > row_tstart, row_desc, row_vis;             // strip assembly: per-node descriptors (two int4 per node) ...
+    ob200::DevBuf< int32_t > row_tstart, row_desc;             // strip assembly: per-node descriptors (two int4 per node) ...
     ob200::DevBuf< unsigned char > row_vtab;                   // ... and column tables (576 B per chunk of eight incidences)
 };
 
@@ -97,6 +99,7 @@ struct ob200_elemset : ob200_sched {
     bool has_state = false;
     ob200::DevBuf< double > coords, mat, state;
     ob200::DevBuf< double > tangent;               // [nelem][36] material tangents of the LTRSpace node-row assembly (sets with a MisesMat)
+    ob200::DevBuf< double > fvis;                  // [nvisit][3] nodal forces of the elements in incidence order (owner-computes vector assembly)
     ob200::DevBuf< double > kebuf;                 // [nvisit][3][24] element-matrix strips of the strip assembly, in incidence order
     ob200::DevBuf< int32_t > conn, matid, loc;
     ob200_csr *bound = nullptr;

@@ -330,6 +330,53 @@ def test_lspace_element_matrix_kernels_agree(ctx, monkeypatch):
     assert relerr(k1, k2) < 1e-14
 
 
+@pytest.mark.parametrize("etype", ["lspace", "ltrspace"])
+def test_owner_computes_internal_force_assembly(ctx, etype, monkeypatch):
+    """EngngModel::assembleVector with InternalForceAssembler without atomics (node_force_gather_kernel): against the oracle
+    (vector and element-by-element norms), against the atomic scatter (OB200_VECTOR_ASSEMBLY=atomic), accumulating into a
+    non-zero vector, and bit-identical run to run.  Irregular numbering, MisesMat + IsoLE."""
+    monkeypatch.delenv("OB200_VECTOR_ASSEMBLY", raising=False)
+    m0 = Material("misesmat", 210e3, 0.3, sig0=240.0, H=2100.0, omega_crit=0.2, a=30.0)
+    pb = _random_problem(etype, 7, 4, 3, seed=33, mat=m0)
+    rng = np.random.default_rng(5)
+    nnode, nelem = pb.coords.shape[0], pb.conn.shape[0]
+    perm = rng.permutation(nnode)
+    coords = np.empty_like(pb.coords)
+    coords[perm] = pb.coords
+    pb.coords, pb.conn = coords, np.ascontiguousarray((perm[pb.conn - 1] + 1).astype(np.int32)[rng.permutation(nelem)])
+    for bc in pb.bcs:
+        bc.nodes = perm[bc.nodes - 1] + 1
+    for ld in pb.loads:
+        ld.nodes = perm[ld.nodes - 1] + 1
+    pb.materials = [m0, Material("isole", 70e3, 0.2)]
+    pb.elem_mat = rng.integers(0, 2, size=nelem).astype(np.int32)
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    u = rng.normal(size=pb.coords.shape) * 5e-3
+    fe_o = orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, u[pb.conn - 1].reshape(nelem, -1), md.state)
+    f_o = orc.assemble_vector(md.loc, fe_o, md.neq)
+    ebe_o = (fe_o.reshape(nelem, -1, 3) ** 2).sum(axis=(0, 1))
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    f, ebe = np.zeros(dom.neq), np.zeros(3)
+    dom.elems.assembleInternalForces(u, f, ebe)
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    assert any(n.startswith("node_force_gather_kernel") for n in prof) and any(n.startswith("norm_finish_kernel") for n in prof), sorted(prof)
+    assert relerr(f, f_o) < TOL_KE and relerr(ebe, ebe_o) < TOL_KE
+    f2, ebe2 = np.zeros(dom.neq), np.zeros(3)
+    dom.elems.assembleInternalForces(u, f2, ebe2)
+    assert np.array_equal(f, f2) and np.array_equal(ebe, ebe2), "owner-computes vector assembly is not bit-reproducible"
+    base = rng.normal(size=dom.neq)
+    f3 = base.copy()
+    dom.elems.assembleInternalForces(u, f3)                       # adds to what is there
+    assert relerr(f3 - base, f_o) < 1e-10
+    monkeypatch.setenv("OB200_VECTOR_ASSEMBLY", "atomic")
+    f4, ebe4 = np.zeros(dom.neq), np.zeros(3)
+    dom.elems.assembleInternalForces(u, f4, ebe4)
+    assert relerr(f4, f) < 1e-13 and relerr(ebe4, ebe) < 1e-13
+
+
 def test_extrapolated_forces_vs_oracle(ctx):
     pb = _random_problem("lspace", 6, 3, 3, seed=9, mat=Material("isole", 70e3, 0.25))
     md = orc.Model(pb)
