@@ -4,6 +4,7 @@
 // (src/core/engngm.C:889-929) over StructuralElement::computeStiffnessMatrix and
 // giveInternalForcesVector (src/sm/Elements/structuralelement.C:575-643, 724-802).
 #include "element_device.cuh"
+#include "element_forces.cuh"
 #include "elemset.h"
 #include <stdlib.h>
 #include <string.h>
@@ -14,7 +15,7 @@ namespace ob200 {
 constexpr int kHexWarps = 8;        // warps (= elements in flight) per CTA for the LSpace kernels
 
 // output modes of the stiffness kernels
-enum { OUT_KE = 0, OUT_CSR = 1, OUT_KDU = 2 };
+enum { OUT_KE = 0, OUT_CSR = 1 };
 
 struct HexShared {
     double xyz[24];          // vertex coordinates
@@ -46,8 +47,7 @@ __device__ __forceinline__ void hex_geometry(HexShared &s, int lane)
 
 template< int MODE >
 __global__ void __launch_bounds__(kHexWarps * 32)
-lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot,
-                        const double *__restrict__ du, int64_t e_begin, int64_t e_end)
+lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot, int64_t e_begin, int64_t e_end)
 {
     __shared__ HexShared sh[kHexWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -58,7 +58,6 @@ lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *
         if ( lane < 24 ) {
             int node = S.conn[e * 8 + lane / 3] - 1;
             s.xyz[lane] = S.coords[(int64_t) node * 3 + lane % 3];
-            if ( MODE == OUT_KDU ) s.ue[lane] = du[(int64_t) node * 3 + lane % 3];
         }
         __syncwarp();
         hex_geometry(s, lane);
@@ -88,7 +87,7 @@ lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *
                 for ( int i = 0; i < 3; i++ )
 #pragma unroll
                     for ( int j = 0; j < 3; j++ ) o[i * 24 + j] = acc[3 * i + j];
-            } else if ( MODE == OUT_CSR ) {
+            } else {
                 const int32_t *sl = slot + e * 576 + ( 3 * a ) * 24 + 3 * b;
 #pragma unroll
                 for ( int i = 0; i < 3; i++ )
@@ -97,93 +96,9 @@ lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *
                         int32_t p = sl[i * 24 + j];
                         if ( p >= 0 ) atomicAdd(out + p, acc[3 * i + j]);
                     }
-            } else {   // f_a += K_ab du_b
-                const int32_t *loc = S.loc + e * 24 + 3 * a;
-#pragma unroll
-                for ( int i = 0; i < 3; i++ ) {
-                    double f = acc[3 * i] * s.ue[3 * b] + acc[3 * i + 1] * s.ue[3 * b + 1] + acc[3 * i + 2] * s.ue[3 * b + 2];
-                    int32_t r = loc[i];
-                    if ( r > 0 && f != 0.0 ) atomicAdd(out + r - 1, f);
-                }
             }
         }
         __syncwarp();
-    }
-}
-
-// Internal forces of LSpace elements.  fe != nullptr: write element vectors [nelem][24];
-// fglob != nullptr: scatter-add into the global vector through loc.
-__global__ void __launch_bounds__(kHexWarps * 32)
-lspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
-                              double *__restrict__ fglob, double *__restrict__ gp_strain,
-                              double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
-                              double *__restrict__ fvis, const int32_t *__restrict__ vis,
-                              int64_t e_begin, int64_t e_end)
-{
-    __shared__ HexShared sh[kHexWarps];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    HexShared &s = sh[wid];
-    double ebe = 0.0;      // sum of f^2 of this lane's dof id over the elements of this warp
-    const int64_t stride = (int64_t) gridDim.x * kHexWarps;
-    for ( int64_t e = e_begin + (int64_t) blockIdx.x * kHexWarps + wid; e < e_end; e += stride ) {
-        if ( lane < 24 ) {
-            int node = S.conn[e * 8 + lane / 3] - 1;
-            s.xyz[lane] = S.coords[(int64_t) node * 3 + lane % 3];
-            s.ue[lane] = u[(int64_t) node * 3 + lane % 3];     // computeVectorOf(VM_Total)
-        }
-        __syncwarp();
-        hex_geometry(s, lane);
-        __syncwarp();
-        const MatParams mp = S.mat[S.matid[e]];
-        if ( lane < 8 ) {
-            const int gp = lane;
-            double eps[6] = { 0, 0, 0, 0, 0, 0 }, sig[6];
-#pragma unroll
-            for ( int k = 0; k < 8; k++ ) strain_add(eps, s.g[gp][k], &s.ue[3 * k]);   // strain = B u
-            if ( mp.type == (double) OB200_MAT_MISES ) {
-                mises_stress(mp, eps, &S.state[e * 8 + gp], sig);
-            } else {
-                double lam, mu;
-                isole_lame(mp.E, mp.nu, lam, mu);
-                iso_stress(lam, mu, eps, sig);          // LinearElasticMaterial::giveRealStressVector_3d
-            }
-#pragma unroll
-            for ( int i = 0; i < 6; i++ ) s.sig[gp][i] = sig[i];
-            if ( gp_strain )
-#pragma unroll
-                for ( int i = 0; i < 6; i++ ) gp_strain[( e * 8 + gp ) * 6 + i] = eps[i];
-            if ( gp_stress )
-#pragma unroll
-                for ( int i = 0; i < 6; i++ ) gp_stress[( e * 8 + gp ) * 6 + i] = sig[i];
-        }
-        __syncwarp();
-        if ( lane < 24 ) {     // answer.plusProduct(B, stress, dV): one dof per lane, Gauss points in order
-            const int k = lane / 3, c = lane % 3;
-            double f = 0.0;
-#pragma unroll
-            for ( int gp = 0; gp < 8; gp++ ) {
-                double fk[3];
-                force_node(fk, s.g[gp][k], s.sig[gp], s.dV[gp]);
-                f += ( c == 0 ? fk[0] : ( c == 1 ? fk[1] : fk[2] ) );
-            }
-            ebe += f * f;
-            if ( fe ) fe[e * 24 + lane] = f;
-            if ( fvis ) fvis[(int64_t) vis[e * 8 + k] * 3 + c] = f;        // owner-computes assembly: node_force_gather_kernel adds them up
-            if ( fglob ) {
-                int32_t r = S.loc[e * 24 + lane];
-                if ( r > 0 ) atomicAdd(fglob + r - 1, f);
-            }
-        }
-        __syncwarp();
-    }
-    if ( ebe_norm2 ) {     // element-by-element norm per dof id (EngngModel::assembleVector eNorms, engngm.C:1108-1133)
-#pragma unroll
-        for ( int c = 0; c < 3; c++ ) {
-            double v = ( lane < 24 && lane % 3 == c ) ? ebe : 0.0;
-#pragma unroll
-            for ( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ( lane == 0 && v != 0.0 ) atomicAdd(ebe_norm2 + c, v);
-        }
     }
 }
 
@@ -224,8 +139,7 @@ __global__ void tet_volume_check_kernel(ElemSetView S, int64_t nelem, int *__res
 
 template< int MODE >
 __global__ void __launch_bounds__(128)
-ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot,
-                          const double *__restrict__ du, int64_t e_begin, int64_t e_end)
+ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *__restrict__ slot, int64_t e_begin, int64_t e_end)
 {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for ( int64_t e = e_begin + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += stride ) {
@@ -251,7 +165,7 @@ ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t
                     for ( int i = 0; i < 3; i++ )
 #pragma unroll
                         for ( int j = 0; j < 3; j++ ) o[i * 12 + j] = acc[3 * i + j];
-                } else if ( MODE == OUT_CSR ) {
+                } else {
                     const int32_t *sl = slot + e * 144 + ( 3 * a ) * 12 + 3 * b;
 #pragma unroll
                     for ( int i = 0; i < 3; i++ )
@@ -260,22 +174,15 @@ ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t
                             int32_t p = sl[i * 12 + j];
                             if ( p >= 0 ) atomicAdd(out + p, acc[3 * i + j]);
                         }
-                } else {
-                    double ub[3] = { du[(int64_t) node[b] * 3], du[(int64_t) node[b] * 3 + 1], du[(int64_t) node[b] * 3 + 2] };
-#pragma unroll
-                    for ( int i = 0; i < 3; i++ ) {
-                        double f = acc[3 * i] * ub[0] + acc[3 * i + 1] * ub[1] + acc[3 * i + 2] * ub[2];
-                        int32_t r = S.loc[e * 12 + 3 * a + i];
-                        if ( r > 0 && f != 0.0 ) atomicAdd(out + r - 1, f);
-                    }
                 }
             }
         }
     }
 }
 
+template< int MODE >       // FORCE_INTERNAL / FORCE_TANGENT_DU (element_forces.cuh)
 __global__ void __launch_bounds__(128)
-ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
+ltrspace_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe,
                                 double *__restrict__ fglob, double *__restrict__ gp_strain,
                                 double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
                                 double *__restrict__ fvis, const int32_t *__restrict__ vis,
@@ -294,13 +201,7 @@ ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, dou
             double ua[3] = { u[(int64_t) node[a] * 3], u[(int64_t) node[a] * 3 + 1], u[(int64_t) node[a] * 3 + 2] };
             strain_add(eps, g[a], ua);
         }
-        if ( mp.type == (double) OB200_MAT_MISES ) {
-            mises_stress(mp, eps, &S.state[e], sig);
-        } else {
-            double lam, mu;
-            isole_lame(mp.E, mp.nu, lam, mu);
-            iso_stress(lam, mu, eps, sig);
-        }
+        point_stress< MODE >(mp, S.state ? &S.state[e] : nullptr, eps, sig);
         if ( gp_strain )
 #pragma unroll
             for ( int i = 0; i < 6; i++ ) gp_strain[e * 6 + i] = eps[i];
@@ -318,7 +219,7 @@ ltrspace_internal_forces_kernel(ElemSetView S, const double *__restrict__ u, dou
                 if ( fvis ) fvis[(int64_t) vis[e * 8 + a] * 3 + i] = fk[i];
                 if ( fglob ) {
                     int32_t r = S.loc[e * 12 + 3 * a + i];
-                    if ( r > 0 ) atomicAdd(fglob + r - 1, fk[i]);
+                    if ( r > 0 && ( MODE == FORCE_INTERNAL || fk[i] != 0.0 ) ) atomicAdd(fglob + r - 1, fk[i]);
                 }
             }
         }
@@ -439,27 +340,25 @@ __global__ void slot_map_kernel(const int32_t *__restrict__ loc, int nd, int64_t
 
 // ---- host side of ob200_elemset ---------------------------------------------------------
 
-static int launch_stiffness(ob200_elemset *S, int mode, double *out, const int32_t *slot, const double *du)
+static int launch_stiffness(ob200_elemset *S, int mode, double *out, const int32_t *slot)
 {
     ob200_context *ctx = S->ctx;
     ElemSetView v = S->view();
     if ( S->nelem == 0 ) return OB200_OK;
     if ( S->etype == OB200_LSPACE ) {
         int grid = ctx->shape.grid(S->nelem * 32, kHexWarps * 32, 4);
-        if ( mode == OUT_KE ) OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_KE >, grid, kHexWarps * 32, 0, v, out, slot, du, 0, S->nelem);
-        else if ( mode == OUT_CSR ) OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_CSR >, grid, kHexWarps * 32, 0, v, out, slot, du, 0, S->nelem);
-        else OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_KDU >, grid, kHexWarps * 32, 0, v, out, slot, du, 0, S->nelem);
+        if ( mode == OUT_KE ) OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_KE >, grid, kHexWarps * 32, 0, v, out, slot, 0, S->nelem);
+        else OB_LAUNCH(ctx, lspace_stiffness_kernel< OUT_CSR >, grid, kHexWarps * 32, 0, v, out, slot, 0, S->nelem);
     } else {
         int grid = ctx->shape.grid(S->nelem, 128, 8);
-        if ( mode == OUT_KE ) OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_KE >, grid, 128, 0, v, out, slot, du, 0, S->nelem);
-        else if ( mode == OUT_CSR ) OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_CSR >, grid, 128, 0, v, out, slot, du, 0, S->nelem);
-        else OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_KDU >, grid, 128, 0, v, out, slot, du, 0, S->nelem);
+        if ( mode == OUT_KE ) OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_KE >, grid, 128, 0, v, out, slot, 0, S->nelem);
+        else OB_LAUNCH(ctx, ltrspace_stiffness_kernel< OUT_CSR >, grid, 128, 0, v, out, slot, 0, S->nelem);
     }
     return OB200_OK;
 }
 
 static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe, double *fglob, double *eps, double *sig,
-                                  double *ebe = nullptr)
+                                  double *ebe = nullptr, int mode = FORCE_INTERNAL)
 {
     ob200_context *ctx = S->ctx;
     ElemSetView v = S->view();
@@ -473,14 +372,19 @@ static int launch_internal_forces(ob200_elemset *S, const double *u, double *fe,
         if ( !S->fvis.p ) OB_CHECK( S->fvis.alloc(S->nvisit * 3) );
         fvis = S->fvis.p;
     }
+    double *fg = gather ? nullptr : fglob, *eb = gather ? nullptr : ebe;
     if ( S->etype == OB200_LSPACE ) {
-        int grid = ctx->shape.grid(S->nelem * 32, kHexWarps * 32, 4);
-        OB_LAUNCH(ctx, lspace_internal_forces_kernel, grid, kHexWarps * 32, 0, v, u, fe, gather ? nullptr : fglob, eps, sig,
-                  gather ? nullptr : ebe, fvis, S->row_vis.p, 0, S->nelem);
+        int grid = ctx->shape.grid(( S->nelem + 3 ) / 4 * 32, kFwWarps * 32, 8);
+        if ( mode == FORCE_INTERNAL )
+            OB_LAUNCH(ctx, lspace_forces_kernel< FORCE_INTERNAL >, grid, kFwWarps * 32, 0, v, u, fe, fg, eps, sig, eb, fvis, S->row_vis.p, S->nelem);
+        else
+            OB_LAUNCH(ctx, lspace_forces_kernel< FORCE_TANGENT_DU >, grid, kFwWarps * 32, 0, v, u, fe, fg, eps, sig, eb, fvis, S->row_vis.p, S->nelem);
     } else {
         int grid = ctx->shape.grid(S->nelem, 128, 8);
-        OB_LAUNCH(ctx, ltrspace_internal_forces_kernel, grid, 128, 0, v, u, fe, gather ? nullptr : fglob, eps, sig,
-                  gather ? nullptr : ebe, fvis, S->row_vis.p, 0, S->nelem);
+        if ( mode == FORCE_INTERNAL )
+            OB_LAUNCH(ctx, ltrspace_forces_kernel< FORCE_INTERNAL >, grid, 128, 0, v, u, fe, fg, eps, sig, eb, fvis, S->row_vis.p, 0, S->nelem);
+        else
+            OB_LAUNCH(ctx, ltrspace_forces_kernel< FORCE_TANGENT_DU >, grid, 128, 0, v, u, fe, fg, eps, sig, eb, fvis, S->row_vis.p, 0, S->nelem);
     }
     if ( gather ) {
         const int64_t nblocks = ( S->nnode + kForceGatherThreads - 1 ) / kForceGatherThreads;
@@ -696,7 +600,7 @@ int ob200_elemset_stiffness(ob200_elemset *S, double *Ke, int on_device)
     if ( S->etype == OB200_LSPACE && !( ke && !strcmp(ke, "dfma") ) && ( reinterpret_cast< uintptr_t >( o.d ) & 15 ) == 0 )
         OB_CHECK( strips_element_matrices(S, o.d, nullptr) );
     else
-        OB_CHECK( launch_stiffness(S, OUT_KE, o.d, nullptr, nullptr) );
+        OB_CHECK( launch_stiffness(S, OUT_KE, o.d, nullptr) );
     return o.finish(S->ctx);
 }
 
@@ -782,7 +686,7 @@ int ob200_elemset_assemble_stiffness(ob200_elemset *S, ob200_csr *A)
     }
     OB_CHECK( build_slot_map(S, A) );
     OB_CHECK( ob200_csr_materialize(A) );
-    OB_CHECK( launch_stiffness(S, OUT_CSR, A->val.p, S->slot.p, nullptr) );
+    OB_CHECK( launch_stiffness(S, OUT_CSR, A->val.p, S->slot.p) );
     ob200_csr_touch(A);
     return OB200_OK;
 }
@@ -816,7 +720,7 @@ int ob200_elemset_assemble_extrapolated_forces(ob200_elemset *S, const double *d
     StagedOut< double > of;
     OB_CHECK( d.stage(S->ctx, du, S->nnode * 3, on_device) );
     OB_CHECK( of.stage(S->ctx, f, S->neq_hint(), on_device, true) );
-    OB_CHECK( launch_stiffness(S, OUT_KDU, of.d, nullptr, d.d) );
+    OB_CHECK( launch_internal_forces(S, d.d, nullptr, of.d, nullptr, nullptr, nullptr, FORCE_TANGENT_DU) );
     return of.finish(S->ctx);
 }
 

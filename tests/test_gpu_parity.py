@@ -377,18 +377,35 @@ def test_owner_computes_internal_force_assembly(ctx, etype, monkeypatch):
     assert relerr(f4, f) < 1e-13 and relerr(ebe4, ebe) < 1e-13
 
 
-def test_extrapolated_forces_vs_oracle(ctx):
-    pb = _random_problem("lspace", 6, 3, 3, seed=9, mat=Material("isole", 70e3, 0.25))
+@pytest.mark.parametrize("etype", ["lspace", "ltrspace"])
+@pytest.mark.parametrize("mat", ["isole", "mises"])
+def test_extrapolated_forces_vs_oracle(ctx, etype, mat):
+    """f += sum_e Ke du_e (StaticStructural::assembleExtrapolatedForces), evaluated as B^T (D B du) dV without forming Ke:
+    against the oracle's element matrices -- for MisesMat the unsymmetric algorithmic tangent of a plastic, uncommitted state."""
+    m = Material("isole", 70e3, 0.25) if mat == "isole" else Material("misesmat", 210e3, 0.3, sig0=240.0, H=2100.0, omega_crit=0.2, a=30.0)
+    pb = _random_problem(etype, 6, 3, 3, seed=9, mat=m)
     md = orc.Model(pb)
     dom = Domain(ctx, pb)
     rng = np.random.default_rng(2)
+    nelem = pb.conn.shape[0]
+    state = None
+    if mat == "mises":
+        u = rng.normal(size=pb.coords.shape) * 6e-3
+        dom.elems.giveInternalForcesVector(u)
+        orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, u[pb.conn - 1].reshape(nelem, -1), md.state)
+        state = md.state
     du = rng.normal(size=pb.coords.shape) * 1e-3
     f = np.zeros(dom.neq)
     dom.elems.assembleExtrapolatedForces(du, f)
-    Ke = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams)
-    due = du[pb.conn - 1].reshape(pb.conn.shape[0], -1)
+    Ke = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, state)
+    if mat == "mises":
+        assert np.abs(Ke - Ke.transpose(0, 2, 1)).max() > 0.0
+    due = du[pb.conn - 1].reshape(nelem, -1)
     ref = orc.assemble_vector(md.loc, np.einsum("eij,ej->ei", Ke, due), md.neq)
     assert relerr(f, ref) < TOL_KE
+    f2 = np.zeros(dom.neq)
+    dom.elems.assembleExtrapolatedForces(du, f2)
+    assert np.array_equal(f, f2)
 
 
 # ---- solver semantics and edge cases -----------------------------------------------------
