@@ -17,6 +17,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "== ncu full"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'spmv_block_kernel|lspace_cluster_kernel|cg_xr_p_kernel' -c 6 \
     -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 1 --cg-iters 2 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+echo "== BASELINE configs 3 (LTRSpace, one partition) and 4 (MisesMat NR) at full size"
+timeout 400 python scripts/run_configs.py ltrspace mises > $OUT/configs_$TAG.jsonl 2> $OUT/configs_$TAG.err; echo "configs rc=$?"; cut -c1-400 $OUT/configs_$TAG.jsonl
 if [ "$2" = "ref" ]; then
 echo "== bench reference arm"
 timeout 1700 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json | head -c 1500; echo
