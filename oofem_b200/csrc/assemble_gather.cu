@@ -1079,12 +1079,11 @@ int gather_bind(ob200_elemset *S, ob200_csr *A)
 int gather_assemble_lspace(ob200_elemset *S, ob200_csr *A)
 {
     ob200_context *ctx = S->ctx;
-    static bool attr_set = false;
+    static unsigned long long attr_set = 0;
     const int smem = (int) sizeof( GatherShared );
-    if ( !attr_set ) {
+    if ( attr_needed(attr_set, ctx->device) ) {
         OB_CUDA( cudaFuncSetAttribute(lspace_gather_kernel< false >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
         OB_CUDA( cudaFuncSetAttribute(lspace_gather_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
-        attr_set = true;
     }
     GatherView G{ S->ninc_start.p, S->ninc.p, S->ninc_node.p, S->nodeeq.p, S->pos.p, S->nblk.p, S->vu.p, S->blk.p, S->gtab.p, S->maxblk };
     ElemSetView v = S->view();

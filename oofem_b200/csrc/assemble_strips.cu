@@ -389,11 +389,10 @@ lspace_rows_kernel(const __grid_constant__ RowsView V, double *__restrict__ val)
 int strips_element_matrices(ob200_elemset *S, double *Ke, const int32_t *vis)
 {
     ob200_context *ctx = S->ctx;
-    static bool attr_set = false;
+    static unsigned long long attr_set = 0;
     const int smem = (int) sizeof( KeShared ) * kKeWarps + kKeMats * ( (int) sizeof( MatParams ) + 4 * (int) sizeof( double ) );
-    if ( !attr_set ) {
+    if ( attr_needed(attr_set, ctx->device) ) {
         OB_CUDA( cudaFuncSetAttribute(lspace_ke_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
-        attr_set = true;
     }
     if ( S->nelem == 0 ) return OB200_OK;
     const int per_sm = 3;                                    // 63.7 KB of shared memory per CTA

@@ -51,6 +51,15 @@ struct LaunchShape {
     }
 };
 
+// cudaFuncSetAttribute is per device: `mask` (one static word per call site) remembers the devices it was done for
+inline bool attr_needed(unsigned long long &mask, int device)
+{
+    const unsigned long long bit = 1ull << ( device & 63 );
+    if ( mask & bit ) return false;
+    mask |= bit;
+    return true;
+}
+
 // The stream of the context the calling thread is working for.  Every C-ABI entry point binds it
 // (bind_stream) before touching device memory: DevBuf allocations are stream-ordered on it.
 struct StreamSlot { cudaStream_t stream = nullptr; };
@@ -149,7 +158,14 @@ struct ob200_context {
 };
 
 namespace ob200 {
-inline void bind_stream(ob200_context *ctx) { current_stream().stream = ctx->stream; }
+// Also makes the context's device current when another one is (a process that drives several devices; with one process
+// per GPU the check never fires): streams, stream-ordered allocations and launches below all belong to ctx->device.
+inline void bind_stream(ob200_context *ctx)
+{
+    current_stream().stream = ctx->stream;
+    int dev = -1;
+    if ( cudaGetDevice(&dev) == cudaSuccess && dev != ctx->device ) cudaSetDevice(ctx->device);
+}
 }
 
 #define OB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \

@@ -295,11 +295,10 @@ static int spmv_block_launch(ob200_csr *A, const int4 *desc, const double *x, do
                              const int *done, const SpmvHalo &hv)
 {
     ob200_context *ctx = A->ctx;
-    static bool attr_set = false;
+    static unsigned long long attr_set = 0;
     const int smem = (int) sizeof( SpmvBlkShared );
-    if ( !attr_set ) {
+    if ( attr_needed(attr_set, ctx->device) ) {
         OB_CUDA( cudaFuncSetAttribute(spmv_block_kernel< MODE >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
-        attr_set = true;
     }
     int grid = ctx->shape.sms * kBlkCtas;
     if ( grid > A->nbchunks ) grid = A->nbchunks;
@@ -328,13 +327,12 @@ static int spmv_launch(ob200_csr *A, const double *x, double *y, double *partial
         return spmv_block_launch< 0 >(A, A->rbdesc.p, x, y, partials, nblocks, done, none);
     }
     if ( A->maxrow <= kSpmvSlack && A->chunks.p ) {
-        static bool attr_set = false;
+        static unsigned long long attr_set = 0;
         const int smem = (int) sizeof( SpmvShared );
-        if ( !attr_set ) {
+        if ( attr_needed(attr_set, ctx->device) ) {
             OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< 0 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
             OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< 1 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
             OB_CUDA( cudaFuncSetAttribute(spmv_stream_kernel< 2 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) );
-            attr_set = true;
         }
         int grid = ctx->shape.sms * 2;                 // persistent: 2 CTAs per SM, 3 stages each in flight
         if ( grid > A->nchunks ) grid = A->nchunks;
