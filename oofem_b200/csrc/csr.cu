@@ -46,13 +46,17 @@ __global__ void fill_incidence_kernel(const int32_t *__restrict__ loc, int64_t n
 
 // One warp per matrix row: gather the equation numbers of all elements touching the row into
 // shared memory, bitonic-sort, drop duplicates.  This is std::set<int> columns[jj-1].insert(ii-1)
-// of compcol.C:178-191 done row-parallel.  FILL = false counts, FILL = true writes colind.
-template< bool FILL >
+// of compcol.C:178-191 done row-parallel.  MODE 0 counts, MODE 1 writes colind (the row is sorted again), MODE 2 counts and keeps
+// the sorted row in a scratch array [neq][tstride] from which row_copy_kernel fills colind once the row starts are known -- the
+// sort, which is the whole cost, then runs once (used when the scratch array is affordable).
+enum { PATTERN_COUNT = 0, PATTERN_FILL = 1, PATTERN_COUNT_KEEP = 2 };
+template< int MODE >
 __global__ void row_pattern_kernel(const int32_t *__restrict__ loc, int nd, int32_t neq,
                                    const int64_t *__restrict__ estart, const int32_t *__restrict__ elems,
                                    int cap, int32_t *__restrict__ rowcount, const int32_t *__restrict__ rowptr,
-                                   int32_t *__restrict__ colind, int *__restrict__ overflow)
+                                   int32_t *__restrict__ colind, int *__restrict__ overflow, int32_t *__restrict__ scratch, int tstride)
 {
+    constexpr bool FILL = MODE == PATTERN_FILL;
     extern __shared__ int32_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int32_t *buf = smem + (size_t) wid * cap;
@@ -96,10 +100,23 @@ __global__ void row_pattern_kernel(const int32_t *__restrict__ loc, int nd, int3
             bool keep = ( v != INT_MAX ) && ( t == 0 || buf[t - 1] != v );
             unsigned m = __ballot_sync(0xffffffffu, keep);
             if ( FILL && keep ) colind[out0 + base + __popc(m & ( ( 1u << lane ) - 1 ))] = v;
+            if ( MODE == PATTERN_COUNT_KEEP && keep ) scratch[row * tstride + base + __popc(m & ( ( 1u << lane ) - 1 ))] = v;
             base += __popc(m);
         }
         if ( !FILL && lane == 0 ) rowcount[row] = base;
         __syncwarp();
+    }
+}
+
+// colind[rowptr[row] + k] = scratch[row][k]: one warp per row
+__global__ void row_copy_kernel(int32_t neq, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ scratch, int tstride,
+                                int32_t *__restrict__ colind)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ( (int64_t) gridDim.x * blockDim.x ) >> 5;
+    for ( int64_t row = ( (int64_t) blockIdx.x * blockDim.x + threadIdx.x ) >> 5; row < neq; row += nwarps ) {
+        const int p0 = rowptr[row], n = rowptr[row + 1] - p0;
+        for ( int k = lane; k < n; k += 32 ) colind[p0 + k] = scratch[row * tstride + k];
     }
 }
 
@@ -477,15 +494,25 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
                "csr_build_structure: an equation couples to %lld candidate entries (> 8192 supported)", (long long) maxcand);
     int warps = cap <= 1024 ? 8 : ( cap <= 4096 ? 4 : 2 );
     size_t smem = (size_t) warps * cap * sizeof( int32_t );
-    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< false >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
-    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< true >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
+    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< PATTERN_COUNT >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
+    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< PATTERN_FILL >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
+    OB_CUDA( cudaFuncSetAttribute(row_pattern_kernel< PATTERN_COUNT_KEEP >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) );
+    // keep the sorted rows of the count pass when the scratch array [neq][maxcand] stays below 6 GB (OB200_PATTERN_KEEP=0: never)
+    DevBuf< int32_t > scratch;
+    const int tstride = (int) maxcand;
+    const char *pk = getenv("OB200_PATTERN_KEEP");
+    const bool keep = neq > 0 && maxcand > 0 && (int64_t) neq * maxcand * 4 <= ( 6ll << 30 ) && !( pk && !strcmp(pk, "0") );
+    if ( keep ) OB_CHECK( scratch.alloc((int64_t) neq * maxcand) );
 
     OB_CHECK( rowcount.alloc(neq + 1) );
     OB_CUDA( cudaMemsetAsync(rowcount.p, 0, sizeof( int32_t ) * ( neq + 1 ), ctx->stream) );
     int pgrid = ctx->shape.grid((int64_t) neq * 32, warps * 32, 4);
-    if ( neq )
-        OB_LAUNCH(ctx, row_pattern_kernel< false >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
-                  rowcount.p, (const int32_t *) nullptr, (int32_t *) nullptr, flag.p + 1);
+    if ( neq && keep )
+        OB_LAUNCH(ctx, row_pattern_kernel< PATTERN_COUNT_KEEP >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
+                  rowcount.p, (const int32_t *) nullptr, (int32_t *) nullptr, flag.p + 1, scratch.p, tstride);
+    else if ( neq )
+        OB_LAUNCH(ctx, row_pattern_kernel< PATTERN_COUNT >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
+                  rowcount.p, (const int32_t *) nullptr, (int32_t *) nullptr, flag.p + 1, (int32_t *) nullptr, 0);
     OB_CHECK( rp64.alloc(neq + 1) );
     int64_t nnz = 0;
     OB_CHECK( exclusive_scan(ctx, rowcount.p, rp64.p, (int64_t) neq + 1, &nnz) );
@@ -502,9 +529,11 @@ int ob200_csr_build_structure(ob200_csr *A, int32_t neq, int64_t nelem, int32_t 
     A->nchunks = nnz > 0 ? (int32_t)( ( nnz - 1 ) / kSpmvChunk + 1 ) : 0;
     OB_CHECK( A->chunks.alloc(A->nchunks + 1) );
     OB_LAUNCH(ctx, spmv_chunk_table_kernel, ctx->shape.grid((int64_t) neq + 1, 256, 8), 256, 0, neq, A->rowptr.p, A->nchunks, A->chunks.p);
-    if ( neq )
-        OB_LAUNCH(ctx, row_pattern_kernel< true >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
-                  (int32_t *) nullptr, A->rowptr.p, A->colind.p, flag.p + 1);
+    if ( neq && keep )
+        OB_LAUNCH(ctx, row_copy_kernel, ctx->shape.grid((int64_t) neq * 32, 256, 8), 256, 0, neq, A->rowptr.p, scratch.p, tstride, A->colind.p);
+    else if ( neq )
+        OB_LAUNCH(ctx, row_pattern_kernel< PATTERN_FILL >, pgrid, warps * 32, smem, L.d, nd, neq, estart.p, elems.p, cap,
+                  (int32_t *) nullptr, A->rowptr.p, A->colind.p, flag.p + 1, (int32_t *) nullptr, 0);
     OB_CUDA( cudaMemsetAsync(A->val.p, 0, sizeof( double ) * (size_t)( nnz + kCsrPad ), ctx->stream) );
     OB_CUDA( cudaMemcpyAsync(hflag, flag.p, sizeof( int ) * 2, cudaMemcpyDeviceToHost, ctx->stream) );
     OB_CUDA( cudaStreamSynchronize(ctx->stream) );

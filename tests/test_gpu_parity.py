@@ -33,12 +33,20 @@ def ctx():
 
 # ---- against the reference's own output ------------------------------------------------
 
+@pytest.mark.parametrize("keep", ["1", "0"])
 @pytest.mark.parametrize("name", LINEAR + MISES)
-def test_csr_structure_bit_exact_vs_reference(ctx, name):
+def test_csr_structure_bit_exact_vs_reference(ctx, name, keep, monkeypatch):
+    """keep = 1: the sorted rows of the count pass are kept and copied (one sort per row); 0: count pass + fill pass."""
+    monkeypatch.setenv("OB200_PATTERN_KEEP", keep)
     pb, d = load_golden(name)
     dom = Domain(ctx, pb)
     A = CudaCSR(ctx)
+    ctx.profile_reset()
+    ctx.set_profiling(True)
     A.buildInternalStructure(dom.loc, dom.neq)
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    assert any(n.startswith("row_copy_kernel") for n in prof) == (keep == "1"), sorted(prof)
     rp, ci = A.structure()
     assert np.array_equal(rp, d["colptr"])
     assert np.array_equal(ci, d["rowind"])
