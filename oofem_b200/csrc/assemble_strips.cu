@@ -419,7 +419,7 @@ int strips_bind(ob200_elemset *S, ob200_csr *A)
               S->ebidx.p, S->nblk.p, S->blk.p, S->maxblk, nchunk.p, (const int32_t *) nullptr, (int4 *) nullptr, (unsigned char *) nullptr);
     int64_t total = 0;
     OB_CHECK( exclusive_scan(ctx, nchunk.p, s64.p, S->nnode + 1, &total) );
-    OB_REQUIRE(total < (int64_t) INT_MAX / kChunkBytes * 4, OB200_ECAPACITY, "strip assembly: %lld chunks exceed the 32-bit chunk index", (long long) total);
+    OB_REQUIRE(total < (int64_t) INT_MAX, OB200_ECAPACITY, "strip assembly: %lld chunks exceed the 32-bit chunk index", (long long) total);
     OB_CHECK( narrow_i64_to_i32(ctx, s64.p, S->row_tstart.p, S->nnode + 1) );
     OB_CHECK( S->row_desc.alloc(S->nnode * 2 * 4) );
     OB_CHECK( S->row_vtab.alloc(( total > 0 ? total : 1 ) * kChunkBytes) );
