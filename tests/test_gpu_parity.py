@@ -338,6 +338,91 @@ def test_lspace_element_matrix_kernels_agree(ctx, monkeypatch):
     assert relerr(k1, k2) < 1e-14
 
 
+def _irregular_hex_problem(mat, nsec=5, nlayers=2, nring=2):
+    """Unstructured LSpace mesh with irregular nodes: `nsec` quadrilateral sectors around a centre line (5 -> the nodes on the line
+    have 5 hexahedra per layer around them, 10 with two layers: more than the 8 of a structured mesh, i.e. more than one chunk of
+    incidences in the strip assembly), `nring` rings of elements, extruded in z; bottom layer clamped."""
+    pts = [(0.0, 0.0)]
+    idx = {}
+    # ring r (1..nring): points on the rays (P) and between the rays (Q); ring 0 is the centre
+    for r in range(1, nring + 1):
+        for k in range(nsec):
+            a = 2 * np.pi * k / nsec
+            idx[("P", r, k)] = len(pts); pts.append((r * np.cos(a), r * np.sin(a)))
+            b = 2 * np.pi * (k + 0.5) / nsec
+            idx[("Q", r, k)] = len(pts); pts.append((1.25 * r * np.cos(b), 1.25 * r * np.sin(b)))
+    quads = []
+    for k in range(nsec):
+        k1 = (k + 1) % nsec
+        quads.append((0, idx[("P", 1, k1)], idx[("Q", 1, k)], idx[("P", 1, k)]))                       # clockwise seen from +z
+        for r in range(1, nring):
+            # two quads per sector and ring: P_r,k - Q_r,k - Q_r+1,k - P_r+1,k   and   Q_r,k - P_r,k1 - P_r+1,k1 - Q_r+1,k
+            quads.append((idx[("P", r, k)], idx[("Q", r, k)], idx[("Q", r + 1, k)], idx[("P", r + 1, k)]))
+            quads.append((idx[("Q", r, k)], idx[("P", r, k1)], idx[("P", r + 1, k1)], idx[("Q", r + 1, k)]))
+    n2 = len(pts)
+    coords = np.array([(x, y, 0.8 * z) for z in range(nlayers + 1) for (x, y) in pts])
+    conn = []
+    for z in range(nlayers):
+        for q in quads:
+            conn.append([v + (z + 1) * n2 + 1 for v in q] + [v + z * n2 + 1 for v in q])
+    conn = np.array(conn, dtype=np.int32)
+    pb = Problem(engng="linearstatic", params=dict(nsteps=1, lstol=1e-13, lsiter=50000, lsprecond=1), coords=coords, elem_type="lspace",
+                 conn=conn, elem_mat=np.zeros(conn.shape[0], np.int32), materials=[mat])
+    pb.ltfs[1] = ("const", 1.0)
+    pb.bcs.append(DirichletBC([1, 2, 3], [0.0, 0.0, 0.0], 1, np.arange(1, n2 + 1)))
+    pb.loads.append(NodalLoad([1, 2, 3], [0.1, 0.2, -1.0], 1, np.arange(nlayers * n2 + 1, (nlayers + 1) * n2 + 1)))
+    return pb
+
+
+@pytest.mark.parametrize("mat,path", [("isole", "cluster"), ("isole", "gather"), ("isole", "strips"), ("mises", None)])
+def test_irregular_nodes_more_than_eight_elements_vs_oracle(ctx, mat, path, monkeypatch):
+    """Nodes with 10 hexahedra around them (and a mix of 2, 4, 5, 8): every LSpace assembly kernel, the force kernels and the
+    solve against the oracle."""
+    if path in (None, "cluster"):
+        monkeypatch.delenv("OB200_ASSEMBLY", raising=False)
+    else:
+        monkeypatch.setenv("OB200_ASSEMBLY", path)
+    m = Material("isole", 210e3, 0.3) if mat == "isole" else Material("misesmat", 210e3, 0.3, sig0=240.0, H=2100.0, omega_crit=0.2, a=30.0)
+    pb = _irregular_hex_problem(m)
+    md = orc.Model(pb)
+    nelem = pb.conn.shape[0]
+    inc = np.bincount(pb.conn.reshape(-1) - 1)
+    assert inc.max() == 10
+    dom = Domain(ctx, pb)
+    rng = np.random.default_rng(8)
+    state = None
+    u = rng.normal(size=pb.coords.shape) * (6e-3 if mat == "mises" else 1e-3)
+    f, ebe = np.zeros(dom.neq), np.zeros(3)
+    dom.elems.assembleInternalForces(u, f, ebe)
+    fe_o = orc.batch_internal_forces(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, u[pb.conn - 1].reshape(nelem, -1), md.state)
+    assert relerr(f, orc.assemble_vector(md.loc, fe_o, md.neq)) < TOL_KE
+    assert relerr(ebe, (fe_o.reshape(nelem, -1, 3) ** 2).sum(axis=(0, 1))) < TOL_KE
+    if mat == "mises":
+        state = md.state
+    Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams, state)
+    assert relerr(dom.elems.computeStiffnessMatrix(), Ke_o) < TOL_KE
+    val_o = orc.compcol_assemble(md.loc, Ke_o, md.colptr, md.rowind)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    rp, ci = A.structure()
+    assert np.array_equal(rp, md.colptr) and np.array_equal(ci, md.rowind)
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    A.zero()
+    dom.elems.assembleStiffness(A)
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    want = {"cluster": "lspace_cluster_kernel", "gather": "lspace_gather_kernel", "strips": "lspace_rows_kernel", None: "lspace_rows_kernel"}[path]
+    assert any(n.startswith(want) for n in prof), (want, sorted(prof))
+    x = rng.normal(size=dom.neq)
+    assert relerr(A.times(x), orc.compcol_times(md.colptr, md.rowind, val_o, x)) < TOL_KE
+    dom.elems.assembleStiffness(A)
+    assert relerr(A.times(x), 2.0 * orc.compcol_times(md.colptr, md.rowind, val_o, x)) < TOL_KE
+    if mat == "isole":
+        sol = orc.solve_linear_static(pb)
+        assert relerr(LinearStatic(ctx, pb).solveYourselfAt(1.0), sol["u"]) < TOL_U
+
+
 @pytest.mark.parametrize("etype", ["lspace", "ltrspace"])
 def test_owner_computes_internal_force_assembly(ctx, etype, monkeypatch):
     """EngngModel::assembleVector with InternalForceAssembler without atomics (node_force_gather_kernel): against the oracle
