@@ -423,6 +423,36 @@ def test_irregular_nodes_more_than_eight_elements_vs_oracle(ctx, mat, path, monk
         assert relerr(LinearStatic(ctx, pb).solveYourselfAt(1.0), sol["u"]) < TOL_U
 
 
+def test_tetrahedra_fan_beyond_the_table_capacity_vs_oracle(ctx, monkeypatch):
+    """40 tetrahedra around one edge: its two nodes have 40 elements around them, more than the 32 the table-driven LTRSpace kernel
+    holds -- tet_bind must fall back to the table-free kernel for the mesh (not to the slot map), with the same values."""
+    monkeypatch.delenv("OB200_ASSEMBLY", raising=False)
+    monkeypatch.delenv("OB200_TET_ROWS", raising=False)
+    n = 40
+    pts = [(0.0, 0.0, 0.0), (0.0, 0.0, 1.0)] + [(np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), 0.5) for k in range(n)]
+    coords = np.array(pts)
+    conn = np.array([[1, 2, 3 + k, 3 + (k + 1) % n] for k in range(n)], dtype=np.int32)
+    pb = Problem(engng="linearstatic", params=dict(nsteps=1, lstol=1e-13, lsiter=50000, lsprecond=1), coords=coords, elem_type="ltrspace",
+                 conn=conn, elem_mat=np.zeros(n, np.int32), materials=[Material("isole", 210e3, 0.3)])
+    pb.ltfs[1] = ("const", 1.0)
+    pb.bcs.append(DirichletBC([1, 2, 3], [0.0, 0.0, 0.0], 1, np.array([3, 4, 5, 13, 23])))
+    pb.loads.append(NodalLoad([1, 2, 3], [0.1, 0.2, -1.0], 1, np.array([2])))
+    md = orc.Model(pb)
+    dom = Domain(ctx, pb)
+    A = CudaCSR(ctx)
+    A.buildInternalStructure(dom.loc, dom.neq)
+    ctx.profile_reset()
+    ctx.set_profiling(True)
+    dom.elems.assembleStiffness(A)
+    ctx.set_profiling(False)
+    prof = ctx.profile_report()
+    assert any(k.startswith("ltrspace_rows_kernel") for k in prof) and not any(k.startswith(("ltrspace_rows2_kernel", "slot_map_kernel")) for k in prof), sorted(prof)
+    val_o = orc.compcol_assemble(md.loc, orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams), md.colptr, md.rowind)
+    assert relerr(A.values(), val_o) < TOL_KE
+    sol = orc.solve_linear_static(pb)
+    assert relerr(LinearStatic(ctx, pb).solveYourselfAt(1.0), sol["u"]) < TOL_U
+
+
 @pytest.mark.parametrize("etype", ["lspace", "ltrspace"])
 def test_owner_computes_internal_force_assembly(ctx, etype, monkeypatch):
     """EngngModel::assembleVector with InternalForceAssembler without atomics (node_force_gather_kernel): against the oracle
