@@ -97,7 +97,7 @@ lspace_ke_dmma_kernel(ElemSetView S, int nmat, int64_t nelem, const int32_t *__r
         const int gp = lane >> 2, sub = lane & 3;
         // the state of the Gauss point is requested now and used behind the geometry
         MisesTangentIn tin;
-        if ( mises && sub < 3 ) mises_tangent_load(&S.state[e * 8 + gp], sub, tin);
+        if ( mises && sub < 3 ) mises_tangent_load(mises_ref(S, e * 8 + gp), sub, tin);
         const int strip = vis_next;
         if ( e + stride < nelem ) {
             matid_next = S.matid[e + stride];

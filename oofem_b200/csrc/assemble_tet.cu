@@ -148,7 +148,7 @@ tet_tangent_kernel(ElemSetView S, int64_t nelem, double *__restrict__ Dout)
     for ( int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride ) {
         const MatParams mp = S.mat[S.matid[e]];
         double D[36];
-        if ( mp.type == (double) OB200_MAT_MISES ) mises_tangent(mp, &S.state[e], D);
+        if ( mp.type == (double) OB200_MAT_MISES ) mises_tangent(mp, mises_ref(S, e), D);
         else isole_D(mp.E, mp.nu, D);
 #pragma unroll
         for ( int i = 0; i < 36; i++ ) Dout[e * 36 + i] = D[i];

@@ -2,11 +2,16 @@
 // IsotropicLinearElasticMaterial and MisesMat.  Reference lines are cited per function.
 #pragma once
 #include "common.cuh"
+#include "elemset.h"
 
 namespace ob200 {
 
-// Per-Gauss-point MisesMat state (the MisesMatStatus fields the 3D path uses,
-// src/sm/Materials/misesmat.h).  Stored AoS, 29 doubles per Gauss point.
+// Per-Gauss-point MisesMat state (the MisesMatStatus fields the 3D path uses, src/sm/Materials/misesmat.h): 29 doubles per
+// Gauss point.  MisesState is the record as the C ABI exchanges it (ob200_elemset_get_state / set_state: [ngp][29]).  On the device
+// the state is field-major within blocks of 32 Gauss points, state[ngp / 32][29][32]: the lanes of a warp work on consecutive
+// Gauss points, so every access is a coalesced run of doubles (with point-major records the internal-force kernel spent 2.7 of its
+// 3.3 ms at 1M hex on 29 scattered 8-byte accesses per point), and the 29 fields of a block stay within 7.4 KB (a kernel that
+// reads the eight points of one element per warp keeps its DRAM locality).  MisesStateRef is one Gauss point of that array.
 struct MisesState {
     double plStrain[6];
     double kappa;
@@ -19,6 +24,24 @@ struct MisesState {
     double effStress[6];
 };
 static_assert( sizeof( MisesState ) == OB200_MISES_STATE_DOUBLES * sizeof( double ), "state layout" );
+
+struct MisesStateRef {
+    double *b;          // the Gauss point's slot in field 0 of its block
+    __device__ __forceinline__ MisesStateRef(double *state, int64_t g) : b(state + ( g >> 5 ) * ( OB200_MISES_STATE_DOUBLES * 32 ) + ( g & 31 )) {}
+    __device__ __forceinline__ double &f(int k) const { return b[k * 32]; }
+    __device__ __forceinline__ double &plStrain(int i) const { return f(i); }
+    __device__ __forceinline__ double &kappa() const { return f(6); }
+    __device__ __forceinline__ double &damage() const { return f(7); }
+    __device__ __forceinline__ double &tempPlStrain(int i) const { return f(8 + i); }
+    __device__ __forceinline__ double &tempKappa() const { return f(14); }
+    __device__ __forceinline__ double &tempDamage() const { return f(15); }
+    __device__ __forceinline__ double &trialStressDev(int i) const { return f(16 + i); }
+    __device__ __forceinline__ double &trialStressVol() const { return f(22); }
+    __device__ __forceinline__ double &effStress(int i) const { return f(23 + i); }
+};
+
+// Gauss point g (element * ngp + point) of an element set's state
+__device__ __forceinline__ MisesStateRef mises_ref(const ElemSetView &S, int64_t g) { return MisesStateRef(S.state, g); }
 
 struct MatParams {   // [type, E, nu, sig0, H, omega_crit, a, pad]
     double type, E, nu, sig0, H, omega_crit, a, pad;
@@ -155,15 +178,15 @@ __device__ __forceinline__ double dev_norm(const double t[6])   // StructuralMat
 }
 
 // MisesMat::giveRealStressVector_3d + performPlasticityReturn (misesmat.C:161-176, 181-255), hType 0.
-__device__ __forceinline__ void mises_stress(const MatParams &mp, const double strain[6], MisesState *st, double stress[6])
+__device__ __forceinline__ void mises_stress(const MatParams &mp, const double strain[6], const MisesStateRef &st, double stress[6])
 {
     double G = mp.E / ( 2.0 * ( 1.0 + mp.nu ) );
     double K = mp.E / ( 3.0 * ( 1.0 - 2.0 * mp.nu ) );
     double pl[6], dev[6], tdev[6];
-    double kappa = st->kappa;
+    double kappa = st.kappa();
 #pragma unroll
     for ( int i = 0; i < 6; i++ ) {
-        pl[i] = st->plStrain[i];
+        pl[i] = st.plStrain(i);
         dev[i] = strain[i] - pl[i];
     }
     double mean = ( dev[0] + dev[1] + dev[2] ) / 3.0;
@@ -172,8 +195,8 @@ __device__ __forceinline__ void mises_stress(const MatParams &mp, const double s
     tdev[3] = G * dev[3]; tdev[4] = G * dev[4]; tdev[5] = G * dev[5];
     double trialVol = 3.0 * K * mean;
 #pragma unroll
-    for ( int i = 0; i < 6; i++ ) st->trialStressDev[i] = tdev[i];
-    st->trialStressVol = trialVol;
+    for ( int i = 0; i < 6; i++ ) st.trialStressDev(i) = tdev[i];
+    st.trialStressVol() = trialVol;
     double trialS = dev_norm(tdev);
     double yieldValue = sqrt(3.0 / 2.0) * trialS - ( mp.sig0 + mp.H * kappa );
     if ( yieldValue > 0.0 ) {
@@ -188,37 +211,37 @@ __device__ __forceinline__ void mises_stress(const MatParams &mp, const double s
     }
     tdev[0] += trialVol; tdev[1] += trialVol; tdev[2] += trialVol;
     double dam = kappa > 0.0 ? mp.omega_crit * ( 1.0 - exp(-mp.a * kappa) ) : 0.0;   // computeDamageParam (449-456)
-    if ( st->damage > dam ) dam = st->damage;                                        // computeDamage (470-481)
+    if ( st.damage() > dam ) dam = st.damage();                                        // computeDamage (470-481)
 #pragma unroll
     for ( int i = 0; i < 6; i++ ) {
-        st->effStress[i] = tdev[i];
-        st->tempPlStrain[i] = pl[i];
+        st.effStress(i) = tdev[i];
+        st.tempPlStrain(i) = pl[i];
         stress[i] = tdev[i] * ( 1.0 - dam );
     }
-    st->tempKappa = kappa;
-    st->tempDamage = dam;
+    st.tempKappa() = kappa;
+    st.tempDamage() = dam;
 }
 
 // MisesMat::give3dMaterialStiffnessMatrix, TangentStiffness (misesmat.C:493-545)
-__device__ __forceinline__ void mises_tangent(const MatParams &mp, const MisesState *st, double D[36])
+__device__ __forceinline__ void mises_tangent(const MatParams &mp, const MisesStateRef &st, double D[36])
 {
     double G = mp.E / ( 2.0 * ( 1.0 + mp.nu ) );
     isole_D(mp.E, mp.nu, D);
-    double kappa = st->kappa, tempKappa = st->tempKappa;
+    double kappa = st.kappa(), tempKappa = st.tempKappa();
     double dKappa = tempKappa - kappa;
     if ( dKappa <= 0.0 ) return;
     double sigmaY = mp.sig0 + mp.H * kappa;
     double t[6], es[6];
 #pragma unroll
     for ( int i = 0; i < 6; i++ ) {
-        t[i] = st->trialStressDev[i];
-        es[i] = st->effStress[i];
+        t[i] = st.trialStressDev(i);
+        es[i] = st.effStress(i);
     }
     double trialS = dev_norm(t);
     double factor = -2.0 * sqrt(6.0) * G * G / trialS;
     double factor1 = factor * sigmaY / ( ( mp.H + 3.0 * G ) * trialS * trialS );
     double factor2 = factor * dKappa;
-    double omega = st->tempDamage;
+    double omega = st.tempDamage();
     double omegaPrime = tempKappa >= 0.0 ? mp.omega_crit * mp.a * exp(-mp.a * tempKappa) : 0.0;
     double scalar = -omegaPrime * sqrt(6.0) * G / ( 3.0 * G + mp.H ) / trialS;
 #pragma unroll
@@ -236,18 +259,18 @@ __device__ __forceinline__ void mises_tangent(const MatParams &mp, const MisesSt
 struct MisesTangentIn {
     double t[6], ti[2], esi[2], kappa, tempKappa, tempDamage;
 };
-__device__ __forceinline__ void mises_tangent_load(const MisesState *st, int sub, MisesTangentIn &in)
+__device__ __forceinline__ void mises_tangent_load(const MisesStateRef &st, int sub, MisesTangentIn &in)
 {
 #pragma unroll
-    for ( int j = 0; j < 6; j++ ) in.t[j] = st->trialStressDev[j];
+    for ( int j = 0; j < 6; j++ ) in.t[j] = st.trialStressDev(j);
 #pragma unroll
     for ( int n = 0; n < 2; n++ ) {
-        in.ti[n] = st->trialStressDev[2 * sub + n];
-        in.esi[n] = st->effStress[2 * sub + n];
+        in.ti[n] = st.trialStressDev(2 * sub + n);
+        in.esi[n] = st.effStress(2 * sub + n);
     }
-    in.kappa = st->kappa;
-    in.tempKappa = st->tempKappa;
-    in.tempDamage = st->tempDamage;
+    in.kappa = st.kappa();
+    in.tempKappa = st.tempKappa();
+    in.tempDamage = st.tempDamage();
 }
 // G, K: shear and bulk modulus, rh = 1 / (H + 3G) (per material, computed once by the caller).  One division (1 / trialS)
 // instead of the five of mises_tangent: the results agree to round-off.

@@ -17,27 +17,27 @@ enum { FORCE_INTERNAL = 0, FORCE_TANGENT_DU = 1 };
 
 // sigma = D_tangent eps with the tangent of MisesMat::give3dMaterialStiffnessMatrix (misesmat.C:493-545), without forming D:
 // D = ( De + f1 t t^T + f2 Idev ) ( 1 - omega ) + scalar es t^T
-__device__ __forceinline__ void mises_tangent_apply(const MatParams &mp, const MisesState *st, const double eps[6], double sig[6])
+__device__ __forceinline__ void mises_tangent_apply(const MatParams &mp, const MisesStateRef &st, const double eps[6], double sig[6])
 {
     const double G = mp.E / ( 2.0 * ( 1.0 + mp.nu ) );
     double lam, mu;
     isole_lame(mp.E, mp.nu, lam, mu);
     iso_stress(lam, mu, eps, sig);
-    const double kappa = st->kappa, tempKappa = st->tempKappa;
+    const double kappa = st.kappa(), tempKappa = st.tempKappa();
     const double dKappa = tempKappa - kappa;
     if ( dKappa <= 0.0 ) return;
     double t[6], es[6];
 #pragma unroll
     for ( int i = 0; i < 6; i++ ) {
-        t[i] = st->trialStressDev[i];
-        es[i] = st->effStress[i];
+        t[i] = st.trialStressDev(i);
+        es[i] = st.effStress(i);
     }
     const double sigmaY = mp.sig0 + mp.H * kappa;
     const double trialS = dev_norm(t);
     const double factor = -2.0 * sqrt(6.0) * G * G / trialS;
     const double factor1 = factor * sigmaY / ( ( mp.H + 3.0 * G ) * trialS * trialS );
     const double factor2 = factor * dKappa;
-    const double omega = st->tempDamage;
+    const double omega = st.tempDamage();
     const double omegaPrime = tempKappa >= 0.0 ? mp.omega_crit * mp.a * exp(-mp.a * tempKappa) : 0.0;
     const double scalar = -omegaPrime * sqrt(6.0) * G / ( 3.0 * G + mp.H ) / trialS;
     double te = 0.0;
@@ -53,9 +53,10 @@ __device__ __forceinline__ void mises_tangent_apply(const MatParams &mp, const M
 
 // stress of one Gauss point for the two modes
 template< int MODE >
-__device__ __forceinline__ void point_stress(const MatParams &mp, MisesState *st, const double eps[6], double sig[6])
+__device__ __forceinline__ void point_stress(const MatParams &mp, const ElemSetView &S, int64_t gpoint, const double eps[6], double sig[6])
 {
     if ( mp.type == (double) OB200_MAT_MISES ) {
+        const MisesStateRef st = mises_ref(S, gpoint);
         if ( MODE == FORCE_INTERNAL ) mises_stress(mp, eps, st, sig);
         else mises_tangent_apply(mp, st, eps, sig);
     } else {
@@ -77,7 +78,7 @@ struct FwShared {
 // fe: element vectors [nelem][24]; fglob: scatter-add through loc (atomicAdd); fvis: the nodal forces in incidence order for the
 // owner-computes assembly (node_force_gather_kernel); gp_strain / gp_stress [nelem * 8][6]; ebe_norm2[3]: element-by-element norms
 template< int MODE >
-__global__ void __launch_bounds__(kFwWarps * 32)
+__global__ void __launch_bounds__(kFwWarps * 32, 3)
 lspace_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__restrict__ fe, double *__restrict__ fglob,
                      double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ ebe_norm2,
                      double *__restrict__ fvis, const int32_t *__restrict__ vis, int64_t nelem)
@@ -141,7 +142,7 @@ lspace_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__rest
                 strain_add(eps, g[kk], uk);               // strain = B u
             }
             const MatParams mp = S.mat[S.matid[e]];
-            point_stress< MODE >(mp, S.state ? &S.state[e * 8 + gp] : nullptr, eps, sig);
+            point_stress< MODE >(mp, S, e * 8 + gp, eps, sig);
             if ( gp_strain )
 #pragma unroll
                 for ( int i = 0; i < 6; i++ ) gp_strain[( e * 8 + gp ) * 6 + i] = eps[i];

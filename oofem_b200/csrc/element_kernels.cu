@@ -63,7 +63,7 @@ lspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t *
         hex_geometry(s, lane);
         const MatParams mp = S.mat[S.matid[e]];
         const bool mises = ( mp.type == (double) OB200_MAT_MISES );
-        if ( mises && lane < 8 ) mises_tangent(mp, &S.state[e * 8 + lane], s.D[lane]);
+        if ( mises && lane < 8 ) mises_tangent(mp, mises_ref(S, e * 8 + lane), s.D[lane]);
         __syncwarp();
         double lam, mu;
         isole_lame(mp.E, mp.nu, lam, mu);
@@ -151,7 +151,7 @@ ltrspace_stiffness_kernel(ElemSetView S, double *__restrict__ out, const int32_t
         double D[36];
         double lam, mu;
         isole_lame(mp.E, mp.nu, lam, mu);
-        if ( mises ) mises_tangent(mp, &S.state[e], D);
+        if ( mises ) mises_tangent(mp, mises_ref(S, e), D);
 #pragma unroll 1
         for ( int a = 0; a < 4; a++ ) {
 #pragma unroll 1
@@ -201,7 +201,7 @@ ltrspace_forces_kernel(ElemSetView S, const double *__restrict__ u, double *__re
             double ua[3] = { u[(int64_t) node[a] * 3], u[(int64_t) node[a] * 3 + 1], u[(int64_t) node[a] * 3 + 2] };
             strain_add(eps, g[a], ua);
         }
-        point_stress< MODE >(mp, S.state ? &S.state[e] : nullptr, eps, sig);
+        point_stress< MODE >(mp, S, e, eps, sig);
         if ( gp_strain )
 #pragma unroll
             for ( int i = 0; i < 6; i++ ) gp_strain[e * 6 + i] = eps[i];
@@ -301,14 +301,29 @@ __global__ void __launch_bounds__(256) norm_finish_kernel(const double *__restri
 }
 
 // MaterialStatus::updateYourself: temp -> committed
-__global__ void mises_commit_kernel(MisesState *st, int64_t n)
+__global__ void mises_commit_kernel(double *state, int64_t n)
 {
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n ) return;
+    const MisesStateRef st(state, i);
 #pragma unroll
-    for ( int k = 0; k < 6; k++ ) st[i].plStrain[k] = st[i].tempPlStrain[k];
-    st[i].kappa = st[i].tempKappa;
-    st[i].damage = st[i].tempDamage;
+    for ( int k = 0; k < 6; k++ ) st.plStrain(k) = st.tempPlStrain(k);
+    st.kappa() = st.tempKappa();
+    st.damage() = st.tempDamage();
+}
+
+// the state as the C ABI exchanges it, point-major records [n][29], from / to the field-major device array [29][n]
+template< bool TO_RECORDS >
+__global__ void mises_state_transpose_kernel(double *__restrict__ fields, double *__restrict__ records, int64_t n)
+{
+    const int64_t total = n * OB200_MISES_STATE_DOUBLES, stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride ) {
+        const int64_t g = t / OB200_MISES_STATE_DOUBLES;
+        const int k = (int)( t - g * OB200_MISES_STATE_DOUBLES );
+        double &fld = MisesStateRef(fields, g).f(k);
+        if ( TO_RECORDS ) records[t] = fld;
+        else fld = records[t];
+    }
 }
 
 // element -> CSR slot map: slot[e][i*nd+j] = position of A(loc_i, loc_j) in val, -1 if prescribed
@@ -562,7 +577,7 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
         return OB200_ECUDA;
     }
     if ( S->has_state ) {
-        int64_t n = nelem * S->ngp * OB200_MISES_STATE_DOUBLES;
+        int64_t n = ( ( nelem * S->ngp + 31 ) / 32 ) * 32 * OB200_MISES_STATE_DOUBLES;        // whole blocks of 32 Gauss points
         if ( ( rc = S->state.alloc(n) ) < 0 ) { delete S; return rc; }
         if ( n && cudaMemsetAsync(S->state.p, 0, sizeof( double ) * (size_t) n, ctx->stream) != cudaSuccess ) {
             set_error("elemset_create: memset failed");
@@ -730,7 +745,7 @@ int ob200_elemset_commit(ob200_elemset *S)
     OB_REQUIRE(S, OB200_EINVAL, "elemset_commit: null argument");
     if ( !S->has_state ) return OB200_OK;
     int64_t n = S->nelem * S->ngp;
-    if ( n ) OB_LAUNCH(S->ctx, mises_commit_kernel, (int) ceil_div(n, 256), 256, 0, (MisesState *) S->state.p, n);
+    if ( n ) OB_LAUNCH(S->ctx, mises_commit_kernel, (int) ceil_div(n, 256), 256, 0, S->state.p, n);
     return OB200_OK;
 }
 
@@ -739,8 +754,12 @@ int ob200_elemset_get_state(ob200_elemset *S, double *state, int on_device)
     if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && state, OB200_EINVAL, "elemset_get_state: null argument");
     OB_REQUIRE(S->has_state, OB200_EINVAL, "elemset_get_state: element set has no MisesMat state");
-    OB_CUDA( cudaMemcpyAsync(state, S->state.p, sizeof( double ) * (size_t) S->state.n,
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S->ctx->stream) );
+    // the device array is field-major (element_device.cuh); the caller gets the records [ngp][29]
+    const int64_t n = S->nelem * S->ngp;
+    StagedOut< double > o;
+    OB_CHECK( o.stage(S->ctx, state, n * OB200_MISES_STATE_DOUBLES, on_device) );
+    if ( n ) OB_LAUNCH(S->ctx, mises_state_transpose_kernel< true >, S->ctx->shape.grid(n * OB200_MISES_STATE_DOUBLES, 256, 8), 256, 0, S->state.p, o.d, n);
+    OB_CHECK( o.finish(S->ctx) );
     OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
     return OB200_OK;
 }
@@ -750,8 +769,11 @@ int ob200_elemset_set_state(ob200_elemset *S, const double *state, int on_device
     if ( S ) ob200::bind_stream(S->ctx);
     OB_REQUIRE(S && state, OB200_EINVAL, "elemset_set_state: null argument");
     OB_REQUIRE(S->has_state, OB200_EINVAL, "elemset_set_state: element set has no MisesMat state");
-    OB_CUDA( cudaMemcpyAsync(S->state.p, state, sizeof( double ) * (size_t) S->state.n,
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S->ctx->stream) );
+    const int64_t n = S->nelem * S->ngp;
+    Staged< double > in;
+    OB_CHECK( in.stage(S->ctx, state, n * OB200_MISES_STATE_DOUBLES, on_device) );
+    if ( n ) OB_LAUNCH(S->ctx, mises_state_transpose_kernel< false >, S->ctx->shape.grid(n * OB200_MISES_STATE_DOUBLES, 256, 8), 256, 0, S->state.p,
+                       const_cast< double * >( in.d ), n);
     OB_CUDA( cudaStreamSynchronize(S->ctx->stream) );
     return OB200_OK;
 }

@@ -3,7 +3,6 @@
 #include "common.cuh"
 
 namespace ob200 {
-struct MisesState;
 struct MatParams;
 
 // what the element kernels see
@@ -13,7 +12,8 @@ struct ElemSetView {
     const int32_t *matid;      // [nelem], 0-based
     const MatParams *mat;      // [nmat]
     const int32_t *loc;        // [nelem][nd], 1-based, 0 = prescribed
-    MisesState *state;         // [nelem*ngp] or nullptr
+    double *state;             // MisesMat state, [nstate / 32][29][32] (element_device.cuh: MisesStateRef), or nullptr
+    int64_t nstate;            // nelem * ngp
     const double *exyz;        // [nelem][nen*3] vertex coordinates gathered per element (LSpace gather path) or nullptr
 };
 } // namespace ob200
@@ -110,7 +110,7 @@ struct ob200_elemset : ob200_sched {
     ob200::ElemSetView view() const
     {
         return ob200::ElemSetView{ coords.p, conn.p, matid.p, (const ob200::MatParams *) mat.p, loc.p,
-                                   (ob200::MisesState *) state.p, exyz.p };
+                                   state.p, nelem * ngp, exyz.p };
     }
 };
 
