@@ -12,10 +12,13 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 ctx = capi.Context(0)
 dev = torch.device("cuda:0")
 t = lambda a: torch.as_tensor(a, device=dev)
-if what == "mises":
+if what in ("mises", "isole"):
     nx, ny, nz = 250, 64, 64
     coords, conn = meshgen.hex_beam(nx, ny, nz)
     mp = np.array([[capi.MAT_MISES, 210e3, 0.3, 250.0, 2100.0, 0.2, 30.0, 0]], dtype=np.float64)
+    if what == "isole":          # the general-tangent path forced onto a linear elastic set
+        mp = np.array([[capi.MAT_ISOLE, 210e3, 0.3, 0, 0, 0, 0, 0]], dtype=np.float64)
+        os.environ["OB200_ASSEMBLY"] = "strips"
     et = "lspace"
 else:
     nx, ny, nz = 110, 78, 78
