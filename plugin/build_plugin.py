@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """Build OOFEM with the cudacsr / cudacg plugin: plugin/_build/oofem_cuda.
 
-The plugin sources (plugin/*.C) are compiled against the reference's headers; the three-line hook
-(plugin/engngm_hook.patch) is applied to a scratch copy of src/core/engngm.C; everything else is the
+The plugin sources (plugin/*.C) are compiled against the reference's headers; the hooks
+(plugin/engngm_hook.patch, plugin/structengngmodel_hook.patch) are applied to scratch copies of src/core/engngm.C and
+src/sm/EngineeringModels/structengngmodel.C; everything else is the
 reference's own objects as compiled by oracle/build_ref.py (same flags, same oofemenv.h stub), linked
 with liboofem_b200.so.  Nothing is written into /root/reference, no reference source enters the repo.
 
@@ -38,9 +39,11 @@ def main():
     lib = import_module("oofem_b200.build").build()
     os.makedirs(OUT, exist_ok=True)
     os.makedirs(SCRATCH, exist_ok=True)
-    # the hook: patch a scratch copy of engngm.C
+    # the hooks: patch scratch copies of engngm.C and structengngmodel.C
     shutil.copy(os.path.join(REF, "src/core/engngm.C"), os.path.join(SCRATCH, "engngm.C"))
     subprocess.check_call(["patch", "-s", os.path.join(SCRATCH, "engngm.C"), os.path.join(HERE, "engngm_hook.patch")])
+    shutil.copy(os.path.join(REF, "src/sm/EngineeringModels/structengngmodel.C"), os.path.join(SCRATCH, "structengngmodel.C"))
+    subprocess.check_call(["patch", "-s", os.path.join(SCRATCH, "structengngmodel.C"), os.path.join(HERE, "structengngmodel_hook.patch")])
     incs = ["-I" + HERE, "-I" + os.path.join(ROOT, "include"), "-I" + OBJDIR, "-I" + REF, "-I" + os.path.join(REF, "src"),
             "-I" + os.path.join(REF, "src/core"), "-I" + os.path.join(REF, "src/sm"),
             "-I" + os.path.join(REF, "src/core/iml"), "-I" + os.path.join(REF, "src/core/xfem")]
@@ -50,14 +53,14 @@ def main():
                '-D__MODULE_LIST="sm iml cuda"']
     flags = ["-O2", "-std=c++17", "-w", "-fPIC", "-D__SM_MODULE", "-D__IML_MODULE"] + cfgdefs
     objs = []
-    for src in [os.path.join(HERE, f) for f in ("cudacontext.C", "cudacsr.C", "cudacg.C")] + [os.path.join(SCRATCH, "engngm.C")]:
+    for src in [os.path.join(HERE, f) for f in ("cudacontext.C", "cudacsr.C", "cudacg.C")] + [os.path.join(SCRATCH, "engngm.C"), os.path.join(SCRATCH, "structengngmodel.C")]:
         obj = os.path.join(SCRATCH, os.path.basename(src) + ".o")
         r = subprocess.run(["g++", "-c", src, "-o", obj] + flags + incs, capture_output=True, text=True)
         if r.returncode:
             print(r.stderr[-6000:])
             return 1
         objs.append(obj)
-    base = [o for o in ref_objs if not o.endswith("src_core_engngm.C.o")]
+    base = [o for o in ref_objs if not o.endswith(("src_core_engngm.C.o", "src_sm_EngineeringModels_structengngmodel.C.o"))]
     nomain = [o for o in base if not o.endswith("src_main_main.C.o")]
     link = ["-L" + os.path.dirname(lib), "-loofem_b200", "-Wl,-rpath,$ORIGIN/../../oofem_b200", "-ldl", "-lpthread", "-rdynamic"]
     exe = os.path.join(OUT, "oofem_cuda")

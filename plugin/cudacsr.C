@@ -12,7 +12,9 @@
 #include "floatarray.h"
 #include "floatmatrix.h"
 #include "crosssection.h"
+#include "fieldmanager.h"
 #include "gausspoint.h"
+#include "generalboundarycondition.h"
 #include "integrationrule.h"
 #include "material.h"
 #include "timestep.h"
@@ -22,6 +24,7 @@
 #include "sm/Materials/isolinearelasticmaterial.h"
 #include "sm/Materials/misesmat.h"
 #include "sm/Materials/structuralms.h"
+#include "sm/EngineeringModels/structengngmodel.h"
 #include "dof.h"
 #include "dofiditem.h"
 
@@ -29,6 +32,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <typeindex>
 #include <typeinfo>
 
 namespace oofem {
@@ -300,6 +304,10 @@ struct BatchedDomain {
     Domain *domain = nullptr;
     int domainVersion = -1, neq = -1, etype = 0, nen = 0, ngp = 0, nelem = 0, nnode = 0;
     bool tried = false, hasMises = false;
+    std :: type_index scheme = typeid( void );      // numbering the set was built with (loc, neq)
+    // (step number, solution state counter) of the last status synchronisation / commit
+    int syncStep = -1, commitStep = -1;
+    long syncCounter = -1, commitCounter = -1;
     std :: vector< double >matparams;              // the table the set was created with
     std :: vector< Material * >mats;               // row -> material
     std :: vector< double >u;                      // scratch: nodal displacements
@@ -311,6 +319,7 @@ struct BatchedDomain {
             set = nullptr;
         }
         tried = false;
+        syncStep = commitStep = -1;
     }
 
     static bool materialRow(Material *m, GaussPoint *gp, TimeStep *tStep, double row [ OB200_MATPARAM_STRIDE ])
@@ -433,18 +442,26 @@ struct BatchedDomain {
                              "CudaCSR: element set");
         domain = d;
         domainVersion = d->giveSerialNumber();
+        scheme = typeid( s );
         return true;
     }
 
-    /// The set for this domain and numbering, built on first use; nullptr if the domain is not of the accepted kind (or a
-    /// condition the host loops test per element and step does not hold now).
+    /// The set for this domain, built on first use with the numbering of that call; nullptr if the domain is not of the
+    /// accepted kind (or a condition the host loops test per element and step does not hold now).  A call with ANOTHER
+    /// numbering scheme (reactions: EModelDefaultPrescribedEquationNumbering) gets the existing set -- whose location
+    /// arrays are then not the caller's: it must scatter itself -- and never builds or rebuilds one (a rebuild would
+    /// lose the resident material state).
     ob200_elemset *get(EngngModel *eModel, TimeStep *tStep, const UnknownNumberingScheme &s, Domain *d)
     {
         if ( std :: getenv("OOFEM_B200_NO_BATCH") ) {
             return nullptr;
         }
+        const bool own = !set || scheme == std :: type_index( typeid( s ) );
         if ( set && ( domain != d || domainVersion != d->giveSerialNumber() ||
-                      neq != eModel->giveNumberOfDomainEquations(d->giveNumber(), s) ) ) {
+                      ( own && neq != eModel->giveNumberOfDomainEquations(d->giveNumber(), s) ) ) ) {
+            if ( !own ) {
+                return nullptr;
+            }
             this->drop();
         }
         if ( !set ) {
@@ -459,6 +476,20 @@ struct BatchedDomain {
         // the conditions the host loops test per element and step (engngm.C:909-911, 1386-1392)
         for ( auto &elem : d->giveElements() ) {
             if ( elem->giveParallelMode() == Element_remote || !elem->isActivated(tStep) || !eModel->isElementActivated( elem.get() ) ) {
+                return nullptr;
+            }
+        }
+        // stress-independent strains -- temperature or eigenstrain loads, temperature / eigenstrain fields
+        // (StructuralMaterial::computeStressIndependentStrainVector_3d, structuralmaterial.C:2268-2340) -- enter the host's
+        // stresses and internal forces; the resident kernels do not evaluate them: such a domain keeps the host loops
+        for ( auto &bc : d->giveBcs() ) {
+            const bcValType vt = bc->giveBCValType();
+            if ( vt == TemperatureBVT || vt == EigenstrainBVT ) {
+                return nullptr;
+            }
+        }
+        if ( FieldManager *fm = eModel->giveContext()->giveFieldManager() ) {
+            if ( fm->isFieldRegistered(FT_Temperature) || fm->isFieldRegistered(FT_EigenStrain) ) {
                 return nullptr;
             }
         }
@@ -499,6 +530,8 @@ std :: map< Domain *, BatchedDomain > &batchedDomains()
 
 int CudaCSR :: batchedVectorCalls = 0;
 int CudaCSR :: batchedUpdateCalls = 0;
+int CudaCSR :: batchedStateCalls = 0;
+int CudaCSR :: batchedReactionCalls = 0;
 
 bool CudaCSR :: assembleBatched(EngngModel *eModel, TimeStep *tStep, const MatrixAssembler &ma,
                                 const UnknownNumberingScheme &s, Domain *domain)
@@ -531,32 +564,150 @@ bool batchedAssembleVector(EngngModel *eModel, FloatArray &answer, TimeStep *tSt
                            const UnknownNumberingScheme &s, Domain *domain, FloatArray *eNorms)
 {
     // internal forces of the total state only: InternalForceAssembler::vectorFromElement asks the element for
-    // InternalForcesVector (StructuralElement::giveInternalForcesVector, useUpdatedGpRecord = 0)
-    if ( typeid( va ) != typeid( InternalForceAssembler ) || mode != VM_Total ) {
+    // InternalForcesVector (StructuralElement::giveInternalForcesVector, useUpdatedGpRecord = 0);
+    // LastEquilibratedInternalForceAssembler (StructuralEngngModel::computeReaction, structengngmodel.C:183-201) for the same
+    // integral over the stresses stored in the committed statuses (useUpdatedGpRecord = 1, structuralelement.C:926-930)
+    const bool last = typeid( va ) == typeid( LastEquilibratedInternalForceAssembler );
+    if ( !( last || typeid( va ) == typeid( InternalForceAssembler ) ) || mode != VM_Total ) {
         return false;
     }
     auto it = batchedDomains().find(domain);
     if ( it == batchedDomains().end() ) {
         return false;                               // no cudacsr matrix on this domain: not our job
     }
-    CudaPhaseTimer timer("assemble_vector_s");
+    CudaPhaseTimer timer(last ? "reaction_forces_s" : "assemble_vector_s");
     BatchedDomain &bd = it->second;
     ob200_elemset *set = bd.get(eModel, tStep, s, domain);
-    if ( !set || answer.giveSize() != bd.neq ) {
+    if ( !set ) {
         return false;
     }
-    double ebe [ 3 ] = { 0., 0., 0. };
-    CudaContext :: check(ob200_elemset_assemble_internal_forces(set, bd.displacements(mode, tStep), answer.givePointer(),
-                                                                eNorms ? ebe : nullptr, 0), "batched internal forces");
-    if ( eNorms ) {
-        for ( int k = 0; k < 3; k++ ) {
-            if ( D_u + k <= eNorms->giveSize() ) {
-                eNorms->at(D_u + k) += ebe [ k ];
+    // the stored stresses are those of the state the resident set committed for this very step: evaluating the
+    // displacements of tStep reproduces them; any other moment (another step, before the update) stays on the host.
+    // With a MisesMat the evaluation would also rewrite the temporary state behind the commit (tempKappa = kappa up to
+    // round-off decides the branch of the next tangent, misesmat.C:507-512): those sets leave the reactions to the host.
+    if ( last && ( bd.hasMises || !( bd.commitStep == tStep->giveNumber() && bd.commitCounter == ( long ) tStep->giveSolutionStateCounter() ) ) ) {
+        return false;
+    }
+    const bool own = bd.scheme == std :: type_index( typeid( s ) );
+    if ( own ) {
+        if ( answer.giveSize() != bd.neq ) {
+            return false;
+        }
+        double ebe [ 3 ] = { 0., 0., 0. };
+        CudaContext :: check(ob200_elemset_assemble_internal_forces(set, bd.displacements(mode, tStep), answer.givePointer(),
+                                                                    eNorms ? ebe : nullptr, 0), "batched internal forces");
+        if ( eNorms ) {
+            for ( int k = 0; k < 3; k++ ) {
+                if ( D_u + k <= eNorms->giveSize() ) {
+                    eNorms->at(D_u + k) += ebe [ k ];
+                }
+            }
+        }
+    } else {
+        // another numbering than the set's (reactions: the prescribed equations): element vectors from the GPU, scattered
+        // here through the caller's location arrays exactly as the host loop does (engngm.C:1396-1407)
+        const int nd = 3 * bd.nen;
+        std :: vector< double >fe( ( size_t ) bd.nelem * nd);
+        CudaContext :: check(ob200_elemset_internal_forces(set, bd.displacements(mode, tStep), fe.data(), nullptr, nullptr, 0),
+                             "batched internal forces (element vectors)");
+        FloatArray charVec(nd);
+        IntArray loc, dofids;
+        for ( int e = 1; e <= bd.nelem; e++ ) {
+            va.locationFromElement(loc, * domain->giveElement(e), s, & dofids);
+            if ( loc.giveSize() != nd ) {
+                OOFEM_ERROR("batched internal forces: element %d has %d location entries, %d expected", e, loc.giveSize(), nd);
+            }
+            bool any = eNorms != nullptr;
+            for ( int k = 0; k < nd && !any; k++ ) {
+                any = loc [ k ] != 0;
+            }
+            if ( !any ) {
+                continue;
+            }
+            for ( int k = 0; k < nd; k++ ) {
+                charVec [ k ] = fe [ ( size_t ) ( e - 1 ) * nd + k ];
+            }
+            answer.assemble(charVec, loc);
+            if ( eNorms ) {
+                eNorms->assembleSquared(charVec, dofids);
             }
         }
     }
-    if ( CudaCSR :: batchedVectorCalls++ == 0 ) {
+    if ( last ) {
+        if ( CudaCSR :: batchedReactionCalls++ == 0 ) {
+            OOFEM_LOG_INFO("CudaCSR: batched reaction forces on the GPU (%d elements)\n", bd.nelem);
+        }
+    } else if ( CudaCSR :: batchedVectorCalls++ == 0 ) {
         OOFEM_LOG_INFO("CudaCSR: batched internal forces on the GPU (%d elements)\n", bd.nelem);
+    }
+    return true;
+}
+
+namespace {
+/// Strains, stresses (and the MisesMat variables) of the current solution into the temporary statuses of the host elements:
+/// what StructuralElement::updateInternalState leaves there (structuralelement.C:960-972); Element::updateYourself commits
+/// them (structuralelement.C:944, misesmat.C:672-690) and the output modules read them.
+void syncStatuses(BatchedDomain &bd, TimeStep *tStep)
+{
+    Domain *domain = bd.domain;
+    const size_t ngpt = ( size_t ) bd.nelem * bd.ngp;
+    std :: vector< double >eps(ngpt * 6), sig(ngpt * 6), state;
+    CudaContext :: check(ob200_elemset_internal_forces(bd.set, bd.displacements(VM_Total, tStep), nullptr, eps.data(), sig.data(), 0),
+                         "batched update: strains and stresses");
+    if ( bd.hasMises ) {
+        state.resize(ngpt * OB200_MISES_STATE_DOUBLES);
+        CudaContext :: check(ob200_elemset_get_state(bd.set, state.data(), 0), "batched update: material state");
+    }
+    FloatArray v6(6);
+    for ( int e = 1; e <= bd.nelem; e++ ) {
+        Element *elem = domain->giveElement(e);
+        IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
+        for ( int g = 0; g < bd.ngp; g++ ) {
+            GaussPoint *gp = iRule->getIntegrationPoint(g);
+            Material *m = elem->giveCrossSection()->giveMaterial(gp);
+            auto *st = static_cast< StructuralMaterialStatus * >( m->giveStatus(gp) );
+            const size_t o = ( ( size_t ) ( e - 1 ) * bd.ngp + g );
+            for ( int k = 0; k < 6; k++ ) v6 [ k ] = eps [ o * 6 + k ];
+            st->letTempStrainVectorBe(v6);
+            for ( int k = 0; k < 6; k++ ) v6 [ k ] = sig [ o * 6 + k ];
+            st->letTempStressVectorBe(v6);
+            if ( bd.hasMises && !std :: strcmp(m->giveClassName(), "MisesMat") ) {
+                // layout of ob200 MisesState: plStrain[6] kappa damage tempPlStrain[6] tempKappa tempDamage
+                // trialStressDev[6] trialStressVol effStress[6]
+                const double *q = & state [ o * OB200_MISES_STATE_DOUBLES ];
+                auto *ms = static_cast< MisesMatStatus * >( st );
+                for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 8 + k ];
+                ms->letTempPlasticStrainBe(v6);
+                ms->setTempCumulativePlasticStrain(q [ 14 ]);
+                ms->setTempDamage(q [ 15 ]);
+                for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 16 + k ];
+                ms->letTrialStressDevBe(v6);
+                ms->setTrialStressVol(q [ 22 ]);
+                for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 23 + k ];
+                ms->letTempEffectiveStressBe(v6);
+            }
+        }
+    }
+    bd.syncStep = tStep->giveNumber();
+    bd.syncCounter = ( long ) tStep->giveSolutionStateCounter();
+}
+} // namespace
+
+bool batchedInternalState(EngngModel *eModel, TimeStep *tStep, Domain *domain)
+{
+    auto it = batchedDomains().find(domain);
+    if ( it == batchedDomains().end() || !it->second.set || CudaCSR :: batchedVectorCalls == 0 ||
+         std :: getenv("OOFEM_B200_NO_STATUS_SYNC") ) {
+        return false;           // the resident material state is only current if the internal forces went through the set
+    }
+    BatchedDomain &bd = it->second;
+    if ( !bd.get(eModel, tStep, EModelDefaultEquationNumbering(), domain) ) {
+        return false;
+    }
+    CudaPhaseTimer timer("status_update_s");
+    syncStatuses(bd, tStep);
+    if ( CudaCSR :: batchedStateCalls++ == 0 ) {
+        OOFEM_LOG_INFO("CudaCSR: batched internal state update on the GPU (%d elements)\n", bd.nelem);
     }
     return true;
 }
@@ -569,51 +720,17 @@ void batchedUpdate(EngngModel *eModel, TimeStep *tStep, Domain *domain)
     }
     CudaPhaseTimer timer("status_update_s");
     BatchedDomain &bd = it->second;
-    // Strains, stresses (and the MisesMat variables) of the converged state into the temporary statuses of the host
-    // elements: Element::updateYourself, which runs next, commits them (structuralelement.C:944, misesmat.C:672-690),
-    // and the output modules read them.  OOFEM_B200_NO_STATUS_SYNC=1 skips the copy (no element output then).
-    if ( !std :: getenv("OOFEM_B200_NO_STATUS_SYNC") ) {
-        const size_t ngpt = ( size_t ) bd.nelem * bd.ngp;
-        std :: vector< double >eps(ngpt * 6), sig(ngpt * 6), state;
-        CudaContext :: check(ob200_elemset_internal_forces(bd.set, bd.displacements(VM_Total, tStep), nullptr, eps.data(), sig.data(), 0),
-                             "batched update: strains and stresses");
-        if ( bd.hasMises ) {
-            state.resize(ngpt * OB200_MISES_STATE_DOUBLES);
-            CudaContext :: check(ob200_elemset_get_state(bd.set, state.data(), 0), "batched update: material state");
-        }
-        FloatArray v6(6);
-        for ( int e = 1; e <= bd.nelem; e++ ) {
-            Element *elem = domain->giveElement(e);
-            IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
-            for ( int g = 0; g < bd.ngp; g++ ) {
-                GaussPoint *gp = iRule->getIntegrationPoint(g);
-                Material *m = elem->giveCrossSection()->giveMaterial(gp);
-                auto *st = static_cast< StructuralMaterialStatus * >( m->giveStatus(gp) );
-                const size_t o = ( ( size_t ) ( e - 1 ) * bd.ngp + g );
-                for ( int k = 0; k < 6; k++ ) v6 [ k ] = eps [ o * 6 + k ];
-                st->letTempStrainVectorBe(v6);
-                for ( int k = 0; k < 6; k++ ) v6 [ k ] = sig [ o * 6 + k ];
-                st->letTempStressVectorBe(v6);
-                if ( bd.hasMises && !std :: strcmp(m->giveClassName(), "MisesMat") ) {
-                    // layout of ob200 MisesState: plStrain[6] kappa damage tempPlStrain[6] tempKappa tempDamage
-                    // trialStressDev[6] trialStressVol effStress[6]
-                    const double *q = & state [ o * OB200_MISES_STATE_DOUBLES ];
-                    auto *ms = static_cast< MisesMatStatus * >( st );
-                    for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 8 + k ];
-                    ms->letTempPlasticStrainBe(v6);
-                    ms->setTempCumulativePlasticStrain(q [ 14 ]);
-                    ms->setTempDamage(q [ 15 ]);
-                    for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 16 + k ];
-                    ms->letTrialStressDevBe(v6);
-                    ms->setTrialStressVol(q [ 22 ]);
-                    for ( int k = 0; k < 6; k++ ) v6 [ k ] = q [ 23 + k ];
-                    ms->letTempEffectiveStressBe(v6);
-                }
-            }
-        }
+    // The converged state into the temporary statuses of the host elements, unless StructuralEngngModel::updateInternalState
+    // has just done so for this very state (batchedInternalState).  OOFEM_B200_NO_STATUS_SYNC=1 skips the copy (no element
+    // output then).
+    if ( !std :: getenv("OOFEM_B200_NO_STATUS_SYNC") &&
+         !( bd.syncStep == tStep->giveNumber() && bd.syncCounter == ( long ) tStep->giveSolutionStateCounter() ) ) {
+        syncStatuses(bd, tStep);
     }
     // MaterialStatus::updateYourself for the resident state: temp -> committed
     CudaContext :: check(ob200_elemset_commit(bd.set), "batched update: commit");
+    bd.commitStep = tStep->giveNumber();
+    bd.commitCounter = ( long ) tStep->giveSolutionStateCounter();
     CudaCSR :: batchedUpdateCalls++;
 }
 } // namespace oofem

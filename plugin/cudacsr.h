@@ -71,7 +71,7 @@ public:
     void giveStructure(IntArray &rowptr, IntArray &colind) const;
     bool usesBatchedAssembly() const { return batchedUsed; }
     /// how often the vector hook (internal forces) and the status update ran on the GPU (tests)
-    static int batchedVectorCalls, batchedUpdateCalls;
+    static int batchedVectorCalls, batchedUpdateCalls, batchedStateCalls, batchedReactionCalls;
 };
 } // namespace oofem
 #endif

@@ -127,7 +127,12 @@ def test_stock_executable_output_matches_reference_executable(tmp_path):
     name = "lspace_cantilever"
     r = subprocess.run([EXE, "-f", cuda_input(name, tmp_path)], capture_output=True, text=True, cwd=tmp_path, timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
-    assert "CudaCG" in r.stdout + r.stderr
+    log = r.stdout + r.stderr
+    assert "CudaCG" in log
+    # every per-element host loop of the step is taken by a hook: tangent, internal forces, the strain / stress update of
+    # StructuralEngngModel::updateInternalState and the internal forces of computeReaction (prescribed numbering)
+    for what in ("tangent assembly", "internal forces", "internal state update", "reaction forces"):
+        assert f"batched {what} on the GPU" in log, (what, log[-3000:])
     ours = _numbers(tmp_path / (name + ".out"))
     os.rename(tmp_path / (name + ".out"), tmp_path / "cuda.out")
     r = subprocess.run([REF_EXE, "-f", cuda_input(name, tmp_path, keep=True)], capture_output=True, text=True, cwd=tmp_path, timeout=600)
