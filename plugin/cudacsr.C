@@ -329,6 +329,9 @@ struct BatchedDomain {
         }
         if ( !std :: strcmp(m->giveClassName(), "IsotropicLinearElasticMaterial") ) {
             auto *iso = static_cast< IsotropicLinearElasticMaterial * >( m );
+            if ( m->giveCastingTime() >= 0. ) {
+                return false;                       // reduced stiffness before casting, incremental stress update
+            }                                       // (linearelasticmaterial.C:82-121): host loop
             row [ 0 ] = OB200_MAT_ISOLE;
             row [ 1 ] = iso->giveYoungsModulus();
             row [ 2 ] = iso->givePoissonsRatio();
@@ -409,7 +412,10 @@ struct BatchedDomain {
                 loc [ ( size_t ) ( e - 1 ) * nen * 3 + k ] = l [ k ];
             }
             // the material comes through the cross section (Structural3DElement::computeConstitutiveMatrixAt,
-            // structural3delement.C:99-103); one material per element on this path
+            // structural3delement.C:99-103), a plain SimpleCrossSection forwards to it; one material per element on this path
+            if ( std :: strcmp(elem->giveCrossSection()->giveClassName(), "SimpleCrossSection") ) {
+                return false;
+            }
             Material *m = elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(0) );
             for ( int g = 1; g < ngp; g++ ) {
                 if ( elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(g) ) != m ) {

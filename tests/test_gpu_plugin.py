@@ -142,6 +142,27 @@ def test_stock_executable_output_matches_reference_executable(tmp_path):
     assert np.abs(ours - ref).max() <= 1e-6 * np.abs(ref).max()    # the .out prints ~5 significant digits
 
 
+def test_temperature_load_keeps_the_host_loops(tmp_path):
+    """lspace_cantilever with a StructTemperatureLoad on every element (tests/golden/lspace_thermal.in): the thermal strain
+    enters the host's stresses and internal forces through computeStressIndependentStrainVector_3d
+    (structuralmaterial.C:2268-2340), which the resident kernels do not evaluate -- every batched hook must decline, the
+    element loops run on the host into cudacsr / cudacg, and the .out equals the reference executable's."""
+    need(EXE)
+    need(REF_EXE)
+    name = "lspace_thermal"
+    r = subprocess.run([EXE, "-f", cuda_input(name, tmp_path)], capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-3000:]
+    assert "CudaCG" in log and "batched" not in log, log[-3000:]
+    ours = _numbers(tmp_path / (name + ".out"))
+    os.rename(tmp_path / (name + ".out"), tmp_path / "cuda.out")
+    r = subprocess.run([REF_EXE, "-f", cuda_input(name, tmp_path, keep=True)], capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    ref = _numbers(tmp_path / (name + ".out"))
+    assert ours.size == ref.size and ours.size > 500
+    assert np.abs(ours - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
 def _element_output(fn):
     """Numbers of the element records (strains, stresses, status variables per Gauss point) of an .out file."""
     txt = open(fn).read()
