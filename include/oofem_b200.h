@@ -128,6 +128,14 @@ int  ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const do
                           int64_t nelem, const int32_t *conn, const int32_t *matid,
                           int32_t nmat, const double *matparams, const int32_t *loc, int32_t neq,
                           int on_device, ob200_elemset **out);
+/* The same set from NODAL equation numbers nodeeq [nnode][3] (1-based, 0 = prescribed; dofs D_u, D_v, D_w of every
+ * node -- DofManager::giveLocationArray, src/core/dofmanager.C) instead of per-element location arrays:
+ * loc[e][3a+i] = nodeeq[conn[e][a]][i] is formed on the device, as Element::giveLocationArray (src/core/element.C)
+ * forms it on the host.  12 bytes per node cross the bus instead of 12 bytes per element node. */
+int  ob200_elemset_create_nodal(ob200_context *ctx, int etype, int64_t nnode, const double *coords,
+                                int64_t nelem, const int32_t *conn, const int32_t *matid,
+                                int32_t nmat, const double *matparams, const int32_t *nodeeq, int32_t neq,
+                                int on_device, ob200_elemset **out);
 void ob200_elemset_destroy(ob200_elemset *S);
 int64_t ob200_elemset_size(const ob200_elemset *S);
 /* element matrices Ke [nelem][nd*nd] (computeStiffnessMatrix, TangentStiffness) */

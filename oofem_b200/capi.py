@@ -59,6 +59,7 @@ SYMBOLS = {
     "ob200_csr_at": (_int, [_vp, _i32, _i32, C.POINTER(_dbl)]),
     "ob200_csr_version": (_i64, [_vp]),
     "ob200_elemset_create": (_int, [_vp, _int, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _int, _pp]),
+    "ob200_elemset_create_nodal": (_int, [_vp, _int, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _int, _pp]),
     "ob200_elemset_destroy": (None, [_vp]),
     "ob200_elemset_size": (_i64, [_vp]),
     "ob200_elemset_stiffness": (_int, [_vp, _vp, _int]),

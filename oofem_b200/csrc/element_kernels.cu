@@ -461,11 +461,33 @@ static int sched_key(ob200_elemset *S, unsigned long long key[8])
 
 using namespace ob200;
 
-extern "C" {
+// Location arrays from nodal equation numbers: loc[e][3a+i] = nodeeq[conn[e][a]][i] -- what Element::giveLocationArray
+// (src/core/element.C) collects from the dofs D_u, D_v, D_w of the element's nodes.  bad[0] counts connectivity entries
+// outside 1..nnode (their location entries are set to 0).
+__global__ void loc_from_nodeeq_kernel(int64_t nelem, int nen, int64_t nnode, const int32_t *__restrict__ conn,
+                                       const int32_t *__restrict__ nodeeq, int32_t *__restrict__ loc, int *__restrict__ bad)
+{
+    const int64_t n = nelem * nen, stride = (int64_t) gridDim.x * blockDim.x;
+    for ( int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride ) {
+        const int64_t node = (int64_t) conn[t] - 1;
+        int32_t e0 = 0, e1 = 0, e2 = 0;
+        if ( node >= 0 && node < nnode ) {
+            e0 = nodeeq[3 * node];
+            e1 = nodeeq[3 * node + 1];
+            e2 = nodeeq[3 * node + 2];
+        } else {
+            atomicAdd(bad, 1);
+        }
+        loc[3 * t] = e0;
+        loc[3 * t + 1] = e1;
+        loc[3 * t + 2] = e2;
+    }
+}
 
-int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const double *coords, int64_t nelem,
-                         const int32_t *conn, const int32_t *matid, int32_t nmat, const double *matparams,
-                         const int32_t *loc, int32_t neq, int on_device, ob200_elemset **out)
+// loc [nelem][3*nen] or (loc == nullptr) nodeeq [nnode][3]
+static int elemset_create_impl(ob200_context *ctx, int etype, int64_t nnode, const double *coords, int64_t nelem,
+                               const int32_t *conn, const int32_t *matid, int32_t nmat, const double *matparams,
+                               const int32_t *loc, const int32_t *nodeeq, int32_t neq, int on_device, ob200_elemset **out)
 {
     if ( ctx ) ob200::bind_stream(ctx);
     OB_REQUIRE(ctx && out, OB200_EINVAL, "elemset_create: null context/out");
@@ -496,7 +518,27 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
         delete S;
         return rc;
     }
-    if ( nelem > 0 ) {
+    if ( nelem > 0 && !loc ) {
+        // nodal equation numbers: 12 bytes per node travel instead of 4 * nd bytes per element; loc is formed on the device
+        DevBuf< int32_t > ne;
+        DevBuf< int > bad;
+        int hb = 0;
+        if ( ( rc = put(ne, nodeeq, nnode * 3) ) < 0 || ( rc = bad.alloc(1) ) < 0 ) { delete S; return rc; }
+        cudaMemsetAsync(bad.p, 0, sizeof( int ), ctx->stream);
+        loc_from_nodeeq_kernel<<< ctx->shape.grid(nelem * S->nen, 256, 8), 256, 0, ctx->stream >>>(nelem, S->nen, nnode, S->conn.p, ne.p, S->loc.p, bad.p);
+        ctx->launches++;
+        if ( cudaMemcpyAsync(&hb, bad.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+             cudaStreamSynchronize(ctx->stream) != cudaSuccess ) {
+            set_error("elemset_create_nodal: forming the location arrays failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            delete S;
+            return OB200_ECUDA;
+        }
+        if ( hb > 0 ) {
+            set_error("elemset_create_nodal: %d connectivity entries outside 1..%lld", hb, (long long) nnode);
+            delete S;
+            return OB200_EINVAL;
+        }
+    } else if ( nelem > 0 ) {
         cudaError_t e = cudaEventRecord(ctx->copy_event, ctx->stream);                 // the allocation is ordered on the main stream
         if ( e == cudaSuccess ) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0);
         if ( e == cudaSuccess )
@@ -587,6 +629,24 @@ int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const dou
     }
     *out = S;
     return OB200_OK;
+}
+
+extern "C" {
+
+int ob200_elemset_create(ob200_context *ctx, int etype, int64_t nnode, const double *coords, int64_t nelem,
+                         const int32_t *conn, const int32_t *matid, int32_t nmat, const double *matparams,
+                         const int32_t *loc, int32_t neq, int on_device, ob200_elemset **out)
+{
+    OB_REQUIRE(loc || nelem <= 0, OB200_EINVAL, "elemset_create: null location arrays");
+    return elemset_create_impl(ctx, etype, nnode, coords, nelem, conn, matid, nmat, matparams, loc, nullptr, neq, on_device, out);
+}
+
+int ob200_elemset_create_nodal(ob200_context *ctx, int etype, int64_t nnode, const double *coords, int64_t nelem,
+                               const int32_t *conn, const int32_t *matid, int32_t nmat, const double *matparams,
+                               const int32_t *nodeeq, int32_t neq, int on_device, ob200_elemset **out)
+{
+    OB_REQUIRE(nodeeq || nnode <= 0 || nelem <= 0, OB200_EINVAL, "elemset_create_nodal: null nodal equation numbers");
+    return elemset_create_impl(ctx, etype, nnode, coords, nelem, conn, matid, nmat, matparams, nullptr, nodeeq, neq, on_device, out);
 }
 
 void ob200_elemset_destroy(ob200_elemset *S)

@@ -17,7 +17,10 @@ NGP = {capi.LSPACE: 8, capi.LTRSPACE: 1}
 
 
 class ElementSet:
-    def __init__(self, ctx: capi.Context, etype, coords, conn, matid, matparams, loc, neq: int):
+    def __init__(self, ctx: capi.Context, etype, coords, conn, matid, matparams, loc, neq: int, nodeeq=None):
+        """loc [nelem, 3*nen]: the elements' location arrays (Element::giveLocationArray); or loc=None and
+        nodeeq [nnode, 3]: the equation numbers of the dofs D_u, D_v, D_w of every node, from which the library forms
+        the location arrays on the device (ob200_elemset_create_nodal)."""
         self.ctx = ctx
         self.etype = ETYPE[etype] if isinstance(etype, str) else int(etype)
         dev = on_device(coords)
@@ -26,7 +29,8 @@ class ElementSet:
             coords = np.ascontiguousarray(coords, dtype=np.float64)
             conn = np.ascontiguousarray(conn, dtype=np.int32)
             matid = np.ascontiguousarray(matid, dtype=np.int32)
-            loc = np.ascontiguousarray(loc, dtype=np.int32)
+            loc = np.ascontiguousarray(loc, dtype=np.int32) if loc is not None else None
+            nodeeq = np.ascontiguousarray(nodeeq, dtype=np.int32) if nodeeq is not None else None
             matparams_arg = matparams
         else:
             import torch
@@ -35,11 +39,19 @@ class ElementSet:
         self.nen, self.ngp = NEN[self.etype], NGP[self.etype]
         self.nd = 3 * self.nen
         self.neq = int(neq)
-        if self.nelem and (int(conn.shape[1]) != self.nen or int(loc.shape[1]) != self.nd):
+        if (loc is None) == (nodeeq is None):
+            raise capi.OofemB200Error(capi.EINVAL, "give either the location arrays or the nodal equation numbers")
+        if self.nelem and (int(conn.shape[1]) != self.nen or (loc is not None and int(loc.shape[1]) != self.nd)):
             raise capi.OofemB200Error(capi.EINVAL, "connectivity / location array shape does not match the element type")
+        if nodeeq is not None and tuple(nodeeq.shape) != (self.nnode, 3):
+            raise capi.OofemB200Error(capi.EINVAL, "nodal equation numbers must be [nnode, 3]")
         self.h = C.c_void_p()
-        check(lib().ob200_elemset_create(ctx.h, self.etype, self.nnode, ptr(coords), self.nelem, ptr(conn), ptr(matid),
-                                         matparams.shape[0], ptr(matparams_arg), ptr(loc), self.neq, dev, C.byref(self.h)))
+        if loc is not None:
+            check(lib().ob200_elemset_create(ctx.h, self.etype, self.nnode, ptr(coords), self.nelem, ptr(conn), ptr(matid),
+                                             matparams.shape[0], ptr(matparams_arg), ptr(loc), self.neq, dev, C.byref(self.h)))
+        else:
+            check(lib().ob200_elemset_create_nodal(ctx.h, self.etype, self.nnode, ptr(coords), self.nelem, ptr(conn), ptr(matid),
+                                                   matparams.shape[0], ptr(matparams_arg), ptr(nodeeq), self.neq, dev, C.byref(self.h)))
 
     @staticmethod
     def _out(like, shape):

@@ -17,9 +17,11 @@ hc, hn, hl, hm = pin(pb["coords"]), pin(pb["conn"]), pin(pb["loc"]), pin(np.zero
 hb, hx = pin(np.ones(neq)), pin(np.zeros(neq))
 A = CudaCSR(ctx); A.buildInternalStructure(hl, neq)
 solver = CudaCG(ctx, None).initializeFrom(dict(lstol=0.0, lsiter=50, lsprecond=1))
+hq = pin(pb["nodeeq"].astype(np.int32))
+nodal = "--nodal" in sys.argv          # upload nodal equation numbers instead of location arrays (ob200_elemset_create_nodal)
 for rep in range(4):
     t = [time.perf_counter()]
-    S = ElementSet(ctx, "lspace", hc, hn, hm, mp, hl, neq); ctx.sync(); t.append(time.perf_counter())
+    S = ElementSet(ctx, "lspace", hc, hn, hm, mp, None if nodal else hl, neq, nodeeq=hq if nodal else None); ctx.sync(); t.append(time.perf_counter())
     S.bind(A); ctx.sync(); t.append(time.perf_counter())
     A.zero(); S.assembleStiffness(A); ctx.sync(); t.append(time.perf_counter())
     hx[:] = 0; t.append(time.perf_counter())

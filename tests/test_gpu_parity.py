@@ -604,6 +604,47 @@ def test_empty_and_degenerate_inputs(ctx):
     assert np.abs(fe).max() < 1e-12 * np.abs(Ke).max()
 
 
+@pytest.mark.parametrize("etype,dims", [("lspace", (7, 4, 3)), ("ltrspace", (5, 4, 3))])
+def test_element_set_from_nodal_equation_numbers(ctx, etype, dims, monkeypatch):
+    """ob200_elemset_create_nodal: the location arrays formed on the device from nodeeq[nnode][3] are those of
+    Element::giveLocationArray -- tangent and internal forces assembled through such a set are bit-identical to the set
+    created from the host's location arrays (host pointers and device-resident inputs); connectivity outside 1..nnode is
+    an error."""
+    import torch
+    monkeypatch.setenv("OB200_SCHED_CACHE", "0")               # every set builds its own schedule
+    pb = _random_problem(etype, *dims, seed=17, mat=Material("isole", 3.0e4, 0.25))
+    dom = Domain(ctx, pb)
+    u = np.random.default_rng(2).normal(size=pb.coords.shape) * 1e-3
+
+    def through(S):
+        A = CudaCSR(ctx)
+        A.buildInternalStructure(dom.loc, dom.neq)
+        S.assembleStiffness(A)
+        f = np.zeros(dom.neq)
+        S.assembleInternalForces(u, f)
+        return A.values(), f
+
+    v0, f0 = through(dom.elems)
+    md = orc.Model(pb)
+    Ke_o = orc.batch_stiffness(md.etype, pb.conn, pb.coords, pb.elem_mat, md.matparams)
+    assert relerr(v0, orc.compcol_assemble(md.loc, Ke_o, md.colptr, md.rowind)) < TOL_KE
+    S1 = ElementSet(ctx, etype, pb.coords, pb.conn, pb.elem_mat, pb.matparams(), None, dom.neq, nodeeq=dom.nodeeq)
+    v1, f1 = through(S1)
+    assert np.array_equal(v0, v1) and np.array_equal(f0, f1)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+    S2 = ElementSet(ctx, etype, t(pb.coords), t(pb.conn), t(pb.elem_mat), pb.matparams(), None, dom.neq, nodeeq=t(dom.nodeeq.astype(np.int32)))
+    torch.cuda.synchronize()
+    v2, f2 = through(S2)
+    assert np.array_equal(v0, v2) and np.array_equal(f0, f2)
+    bad = pb.conn.copy()
+    bad[1, 2] = pb.coords.shape[0] + 3
+    with pytest.raises(capi.OofemB200Error) as ei:
+        ElementSet(ctx, etype, pb.coords, bad, pb.elem_mat, pb.matparams(), None, dom.neq, nodeeq=dom.nodeeq)
+    assert ei.value.code == capi.EINVAL
+    with pytest.raises(capi.OofemB200Error):                   # both or neither of loc / nodeeq
+        ElementSet(ctx, etype, pb.coords, pb.conn, pb.elem_mat, pb.matparams(), dom.loc, dom.neq, nodeeq=dom.nodeeq)
+
+
 def test_device_resident_inputs(ctx):
     """on_device = 1: torch CUDA tensors are consumed in place (the `value` path of bench.py)."""
     import torch
