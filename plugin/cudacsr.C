@@ -1,5 +1,6 @@
 #include "cudacsr.h"
 #include "cudacontext.h"
+#include "cudaparallel.h"
 
 #include "activebc.h"
 #include "assemblercallback.h"
@@ -58,15 +59,17 @@ int CudaCSR :: buildInternalStructure(EngngModel *eModel, int di, const UnknownN
     // location arrays of the active boundary conditions
     Domain *domain = eModel->giveDomain(di);
     int neq = eModel->giveNumberOfDomainEquations(di, s);
-    std :: vector< IntArray >locs;
-    locs.reserve(domain->giveNumberOfElements() + 8);
-    IntArray loc;
-    int width = 0;
-    for ( auto &elem : domain->giveElements() ) {
-        elem->giveLocationArray(loc, s);
-        width = std :: max(width, loc.giveSize());
-        locs.push_back(loc);
-    }
+    const int nelemAll = domain->giveNumberOfElements();
+    std :: vector< IntArray >locs(nelemAll);
+    locs.reserve(nelemAll + 8);
+    std :: vector< int >widths(cudaPluginThreads(), 0);
+    parallelFor(nelemAll, [ & ](long b, long e, int t) {
+        for ( long i = b; i < e; i++ ) {
+            domain->giveElement( ( int ) i + 1)->giveLocationArray(locs [ i ], s);
+            widths [ t ] = std :: max(widths [ t ], locs [ i ].giveSize());
+        }
+    });
+    int width = * std :: max_element(widths.begin(), widths.end());
     std :: vector< IntArray >r_locs, c_locs;
     for ( auto &gbc : domain->giveBcs() ) {
         ActiveBoundaryCondition *bc = dynamic_cast< ActiveBoundaryCondition * >( gbc.get() );
@@ -84,11 +87,13 @@ int CudaCSR :: buildInternalStructure(EngngModel *eModel, int di, const UnknownN
         }
     }
     std :: vector< int32_t >flat(locs.size() * ( size_t ) std :: max(width, 1), 0);
-    for ( std :: size_t e = 0; e < locs.size(); e++ ) {
-        for ( int k = 0; k < locs [ e ].giveSize(); k++ ) {
-            flat [ e * width + k ] = locs [ e ] [ k ];
+    parallelFor( ( long ) locs.size(), [ & ](long b, long e2, int) {
+        for ( long e = b; e < e2; e++ ) {
+            for ( int k = 0; k < locs [ e ].giveSize(); k++ ) {
+                flat [ ( size_t ) e * width + k ] = locs [ e ] [ k ];
+            }
         }
-    }
+    });
     pendLoc.clear();
     pendMat.clear();
     pendCount = 0;
@@ -379,61 +384,88 @@ struct BatchedDomain {
         matparams.clear();
         mats.clear();
         hasMises = false;
-        IntArray l, ids;
-        FloatMatrix R;
+        // pass 1 (threads): what every element is asked -- class, geometry mode, integration rule, connectivity, location
+        // array with its dof ids, the material behind the cross section
+        std :: vector< Material * >emat(nelem, nullptr);
+        std :: vector< char >reject(cudaPluginThreads(), 0);
+        const int nen_ = nen, ngp_ = ngp;
+        parallelFor(nelem, [ & ](long b, long e2, int t) {
+            IntArray l, ids;
+            FloatMatrix R;
+            for ( long i = b; i < e2 && !reject [ t ]; i++ ) {
+                Element *elem = d->giveElement( ( int ) i + 1);
+                reject [ t ] = 1;                                   // cleared at the end of a clean pass
+                if ( std :: strcmp(elem->giveClassName(), cn) ) {
+                    break;
+                }
+                NLStructuralElement *se = dynamic_cast< NLStructuralElement * >( elem );
+                if ( !se || se->giveGeometryMode() != 0 || elem->giveRotationMatrix(R) ) {
+                    break;
+                }
+                IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
+                if ( !iRule || iRule->giveNumberOfIntegrationPoints() != ngp_ || elem->giveNumberOfIntegrationRules() != 1 ) {
+                    break;
+                }
+                const IntArray &dm = elem->giveDofManArray();
+                if ( dm.giveSize() != nen_ ) {
+                    break;
+                }
+                for ( int k = 0; k < nen_; k++ ) {
+                    conn [ ( size_t ) i * nen_ + k ] = dm [ k ];
+                }
+                elem->giveLocationArray(l, s, & ids);
+                if ( l.giveSize() != 3 * nen_ ) {
+                    break;
+                }
+                bool ok = true;
+                for ( int k = 0; k < 3 * nen_; k++ ) {
+                    ok = ok && ids [ k ] == D_u + k % 3;
+                    loc [ ( size_t ) i * nen_ * 3 + k ] = l [ k ];
+                }
+                if ( !ok ) {
+                    break;
+                }
+                // the material comes through the cross section (Structural3DElement::computeConstitutiveMatrixAt,
+                // structural3delement.C:99-103), a plain SimpleCrossSection forwards to it; one material per element on this path
+                if ( std :: strcmp(elem->giveCrossSection()->giveClassName(), "SimpleCrossSection") ) {
+                    break;
+                }
+                Material *m = elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(0) );
+                for ( int g = 1; g < ngp_ && ok; g++ ) {
+                    ok = elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(g) ) == m;
+                }
+                if ( !ok || !m ) {
+                    break;
+                }
+                emat [ i ] = m;
+                reject [ t ] = 0;
+            }
+        });
+        if ( std :: any_of(reject.begin(), reject.end(), [](char c) { return c != 0; }) ) {
+            return false;
+        }
+        // pass 2 (serial): the parameter table, one row per material in order of first use
+        Material *lastMat = nullptr;
+        int lastRow = -1;
         for ( int e = 1; e <= nelem; e++ ) {
-            Element *elem = d->giveElement(e);
-            if ( std :: strcmp(elem->giveClassName(), cn) ) {
-                return false;
-            }
-            NLStructuralElement *se = dynamic_cast< NLStructuralElement * >( elem );
-            if ( !se || se->giveGeometryMode() != 0 || elem->giveRotationMatrix(R) ) {
-                return false;
-            }
-            IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
-            if ( !iRule || iRule->giveNumberOfIntegrationPoints() != ngp || elem->giveNumberOfIntegrationRules() != 1 ) {
-                return false;
-            }
-            const IntArray &dm = elem->giveDofManArray();
-            if ( dm.giveSize() != nen ) {
-                return false;
-            }
-            for ( int k = 0; k < nen; k++ ) {
-                conn [ ( size_t ) ( e - 1 ) * nen + k ] = dm [ k ];
-            }
-            elem->giveLocationArray(l, s, & ids);
-            if ( l.giveSize() != 3 * nen ) {
-                return false;
-            }
-            for ( int k = 0; k < 3 * nen; k++ ) {
-                if ( ids [ k ] != D_u + k % 3 ) {
-                    return false;
+            Material *m = emat [ e - 1 ];
+            if ( m != lastMat ) {
+                auto found = matIndex.find( m->giveNumber() );
+                if ( found == matIndex.end() ) {
+                    double row [ OB200_MATPARAM_STRIDE ];
+                    GaussPoint *gp0 = d->giveElement(e)->giveDefaultIntegrationRulePtr()->getIntegrationPoint(0);
+                    if ( !materialRow(m, gp0, tStep, row) ) {
+                        return false;
+                    }
+                    hasMises = hasMises || row [ 0 ] == OB200_MAT_MISES;
+                    found = matIndex.insert({ m->giveNumber(), ( int ) matIndex.size() }).first;
+                    matparams.insert(matparams.end(), row, row + OB200_MATPARAM_STRIDE);
+                    mats.push_back(m);
                 }
-                loc [ ( size_t ) ( e - 1 ) * nen * 3 + k ] = l [ k ];
+                lastMat = m;
+                lastRow = found->second;
             }
-            // the material comes through the cross section (Structural3DElement::computeConstitutiveMatrixAt,
-            // structural3delement.C:99-103), a plain SimpleCrossSection forwards to it; one material per element on this path
-            if ( std :: strcmp(elem->giveCrossSection()->giveClassName(), "SimpleCrossSection") ) {
-                return false;
-            }
-            Material *m = elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(0) );
-            for ( int g = 1; g < ngp; g++ ) {
-                if ( elem->giveCrossSection()->giveMaterial( iRule->getIntegrationPoint(g) ) != m ) {
-                    return false;
-                }
-            }
-            auto found = matIndex.find( m->giveNumber() );
-            if ( found == matIndex.end() ) {
-                double row [ OB200_MATPARAM_STRIDE ];
-                if ( !materialRow(m, iRule->getIntegrationPoint(0), tStep, row) ) {
-                    return false;
-                }
-                hasMises = hasMises || row [ 0 ] == OB200_MAT_MISES;
-                found = matIndex.insert({ m->giveNumber(), ( int ) matIndex.size() }).first;
-                matparams.insert(matparams.end(), row, row + OB200_MATPARAM_STRIDE);
-                mats.push_back(m);
-            }
-            matid [ e - 1 ] = found->second;
+            matid [ e - 1 ] = lastRow;
         }
         std :: vector< double >coords( ( size_t ) nnode * 3, 0.);
         for ( int n = 1; n <= nnode; n++ ) {
@@ -480,10 +512,18 @@ struct BatchedDomain {
             }
         }
         // the conditions the host loops test per element and step (engngm.C:909-911, 1386-1392)
-        for ( auto &elem : d->giveElements() ) {
-            if ( elem->giveParallelMode() == Element_remote || !elem->isActivated(tStep) || !eModel->isElementActivated( elem.get() ) ) {
-                return nullptr;
+        std :: vector< char >inactive(cudaPluginThreads(), 0);
+        parallelFor(d->giveNumberOfElements(), [ & ](long b, long e, int t) {
+            for ( long i = b; i < e; i++ ) {
+                Element *elem = d->giveElement( ( int ) i + 1);
+                if ( elem->giveParallelMode() == Element_remote || !elem->isActivated(tStep) || !eModel->isElementActivated(elem) ) {
+                    inactive [ t ] = 1;
+                    return;
+                }
             }
+        }, 65536);
+        if ( std :: any_of(inactive.begin(), inactive.end(), [](char c) { return c != 0; }) ) {
+            return nullptr;
         }
         // stress-independent strains -- temperature or eigenstrain loads, temperature / eigenstrain fields
         // (StructuralMaterial::computeStressIndependentStrainVector_3d, structuralmaterial.C:2268-2340) -- enter the host's
@@ -514,15 +554,17 @@ struct BatchedDomain {
     const double *displacements(ValueModeType mode, TimeStep *tStep)
     {
         u.assign( ( size_t ) nnode * 3, 0.);
-        for ( int n = 1; n <= nnode; n++ ) {
-            DofManager *dman = domain->giveDofManager(n);
-            for ( int k = 0; k < 3; k++ ) {
-                auto it = dman->findDofWithDofId( ( DofIDItem ) ( D_u + k ) );
-                if ( it != dman->end() ) {
-                    u [ ( size_t ) ( n - 1 ) * 3 + k ] = ( * it )->giveUnknown(mode, tStep);
+        parallelFor(nnode, [ & ](long b, long e, int) {
+            for ( long n = b; n < e; n++ ) {
+                DofManager *dman = domain->giveDofManager( ( int ) n + 1);
+                for ( int k = 0; k < 3; k++ ) {
+                    auto it = dman->findDofWithDofId( ( DofIDItem ) ( D_u + k ) );
+                    if ( it != dman->end() ) {
+                        u [ ( size_t ) n * 3 + k ] = ( * it )->giveUnknown(mode, tStep);
+                    }
                 }
             }
-        }
+        }, 16384);
         return u.data();
     }
 };
@@ -616,22 +658,41 @@ bool batchedAssembleVector(EngngModel *eModel, FloatArray &answer, TimeStep *tSt
         std :: vector< double >fe( ( size_t ) bd.nelem * nd);
         CudaContext :: check(ob200_elemset_internal_forces(set, bd.displacements(mode, tStep), fe.data(), nullptr, nullptr, 0),
                              "batched internal forces (element vectors)");
-        FloatArray charVec(nd);
-        IntArray loc, dofids;
-        for ( int e = 1; e <= bd.nelem; e++ ) {
-            va.locationFromElement(loc, * domain->giveElement(e), s, & dofids);
-            if ( loc.giveSize() != nd ) {
-                OOFEM_ERROR("batched internal forces: element %d has %d location entries, %d expected", e, loc.giveSize(), nd);
+        std :: vector< int32_t >locs( ( size_t ) bd.nelem * nd), ids( ( size_t ) bd.nelem * nd);
+        std :: vector< int >badElem(cudaPluginThreads(), 0);
+        parallelFor(bd.nelem, [ & ](long b, long e2, int t) {
+            IntArray loc, dofids;
+            for ( long e = b; e < e2; e++ ) {
+                va.locationFromElement(loc, * domain->giveElement( ( int ) e + 1), s, & dofids);
+                if ( loc.giveSize() != nd || dofids.giveSize() != nd ) {
+                    badElem [ t ] = ( int ) e + 1;
+                    return;
+                }
+                for ( int k = 0; k < nd; k++ ) {
+                    locs [ ( size_t ) e * nd + k ] = loc [ k ];
+                    ids [ ( size_t ) e * nd + k ] = dofids [ k ];
+                }
             }
+        });
+        for ( int be : badElem ) {
+            if ( be ) {
+                OOFEM_ERROR("batched internal forces: element %d does not have %d location entries", be, nd);
+            }
+        }
+        FloatArray charVec(nd);
+        IntArray loc(nd), dofids(nd);
+        for ( int e = 0; e < bd.nelem; e++ ) {
             bool any = eNorms != nullptr;
             for ( int k = 0; k < nd && !any; k++ ) {
-                any = loc [ k ] != 0;
+                any = locs [ ( size_t ) e * nd + k ] != 0;
             }
             if ( !any ) {
                 continue;
             }
             for ( int k = 0; k < nd; k++ ) {
-                charVec [ k ] = fe [ ( size_t ) ( e - 1 ) * nd + k ];
+                charVec [ k ] = fe [ ( size_t ) e * nd + k ];
+                loc [ k ] = locs [ ( size_t ) e * nd + k ];
+                dofids [ k ] = ids [ ( size_t ) e * nd + k ];
             }
             answer.assemble(charVec, loc);
             if ( eNorms ) {
@@ -664,9 +725,12 @@ void syncStatuses(BatchedDomain &bd, TimeStep *tStep)
         state.resize(ngpt * OB200_MISES_STATE_DOUBLES);
         CudaContext :: check(ob200_elemset_get_state(bd.set, state.data(), 0), "batched update: material state");
     }
+    // one contiguous range of elements per thread: the statuses of different Gauss points are independent objects
+    // (created on first use by Material::giveStatus, as in the reference's own parallel element loops)
+    parallelFor(bd.nelem, [ & ](long eb, long ee, int) {
     FloatArray v6(6);
-    for ( int e = 1; e <= bd.nelem; e++ ) {
-        Element *elem = domain->giveElement(e);
+    for ( long e = eb + 1; e <= ee; e++ ) {
+        Element *elem = domain->giveElement( ( int ) e);
         IntegrationRule *iRule = elem->giveDefaultIntegrationRulePtr();
         for ( int g = 0; g < bd.ngp; g++ ) {
             GaussPoint *gp = iRule->getIntegrationPoint(g);
@@ -694,6 +758,7 @@ void syncStatuses(BatchedDomain &bd, TimeStep *tStep)
             }
         }
     }
+    }, 1024);
     bd.syncStep = tStep->giveNumber();
     bd.syncCounter = ( long ) tStep->giveSolutionStateCounter();
 }
