@@ -215,3 +215,5 @@ def test_reference_own_tests_sm_through_the_plugin(name, hooked, tmp_path):
     assert ("CudaCG" in log) == hooked          # Mises01 has no free dof: nothing to solve, the check values still hold
     assert ("batched tangent assembly on the GPU" in log) == hooked, log[-3000:]
     assert ("batched internal forces on the GPU" in log) == hooked, log[-3000:]
+    # the #REACTION values of the CHECK blocks come from computeReaction: internal forces in the prescribed numbering
+    assert ("batched reaction forces on the GPU" in log) == hooked, log[-3000:]

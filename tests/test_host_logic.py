@@ -75,3 +75,57 @@ def test_piecewise_linear_function():
     pb = Problem()
     pb.ltfs[2] = ("pwl", np.array([0.0, 4.0]), np.array([0.0, 1.0]))
     assert pb.ltf_value(2, 1.0) == 0.25 and pb.ltf_value(2, 9.0) == 1.0
+
+
+def test_plugin_parallel_for_covers_every_index_once(tmp_path):
+    """plugin/cudaparallel.h (the std::thread loops of the plugin's host side): every index of [0, n) is visited exactly once,
+    for sizes around the grain and the thread count, with one thread and with several."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "pf.cpp"
+    src.write_text(r'''
+#include "cudaparallel.h"
+#include <cstdio>
+#include <vector>
+int main() {
+    const long sizes[] = { 0, 1, 7, 4095, 4096, 4097, 8192, 65537, 1000003 };
+    for ( long n : sizes ) {
+        std::vector< int > hit(n, 0), threads(64, 0);
+        oofem::parallelFor(n, [ & ](long b, long e, int t) {
+            if ( b > e || b < 0 || e > n || t < 0 || t >= oofem::cudaPluginThreads() ) std::abort();
+            threads[t]++;
+            for ( long i = b; i < e; i++ ) hit[i]++;
+        });
+        for ( long i = 0; i < n; i++ ) if ( hit[i] != 1 ) { std::printf("n=%ld index %ld hit %d times\n", n, i, hit[i]); return 1; }
+        for ( int t : threads ) if ( t > 1 ) { std::printf("thread index used twice\n"); return 1; }
+    }
+    std::printf("ok %d\n", oofem::cudaPluginThreads());
+    return 0;
+}
+''')
+    exe = tmp_path / "pf"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "plugin"), str(src), "-o", str(exe), "-lpthread"])
+    for nthreads in ("1", "3", "16"):
+        r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, OOFEM_B200_THREADS=nthreads))
+        assert r.returncode == 0 and r.stdout.strip() == "ok " + nthreads, (r.stdout, r.stderr)
+
+
+@pytest.mark.parametrize("patch,target", [("engngm_hook.patch", "src/core/engngm.C"),
+                                          ("structengngmodel_hook.patch", "src/sm/EngineeringModels/structengngmodel.C")])
+def test_hook_patches_apply_to_the_reference(patch, target, tmp_path):
+    """The hook sites INTEGRATION.md shows are what plugin/build_plugin.py patches into scratch copies of the reference's files;
+    each patch must apply cleanly and only add lines (plus the loop-bound rename of the vector hook)."""
+    import shutil
+    import subprocess
+    ref = os.environ.get("OOFEM_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box): the prebuilt plugin/_build travels instead")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    work = tmp_path / os.path.basename(target)
+    shutil.copy(os.path.join(ref, target), work)
+    r = subprocess.run(["patch", "-s", str(work), os.path.join(root, "plugin", patch)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    before = open(os.path.join(ref, target)).read().splitlines()
+    after = open(work).read().splitlines()
+    assert 0 < len(after) - len(before) <= 8
+    assert any("batched" in l.lower() for l in after) and not any("batched" in l.lower() for l in before)
