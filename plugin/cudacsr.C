@@ -590,8 +590,8 @@ bool CudaCSR :: assembleBatched(EngngModel *eModel, TimeStep *tStep, const Matri
     CudaPhaseTimer timer("assemble_matrix_s");
     BatchedDomain &bd = batchedDomains() [ domain ];
     ob200_elemset *set = bd.get(eModel, tStep, s, domain);
-    if ( !set ) {
-        return false;
+    if ( !set || bd.scheme != std :: type_index( typeid( s ) ) ) {
+        return false;           // (a set built for another numbering scheme scatters through other location arrays: host loop)
     }
     // MisesMat::give3dMaterialStiffnessMatrix answers the elastic matrix for every mode but TangentStiffness
     // (misesmat.C:496-503); the kernels evaluate the algorithmic tangent
